@@ -1,0 +1,21 @@
+"""B200-native batched minimum-snap trajectory generation + mesh collision checking.
+
+A from-scratch sm_100a implementation of the data-parallel hot path of
+mjmyt/drone_path_planning_python: ``batch`` is the tensor-level
+throughput API over the C ABI in ``include/mst.h``; ``dropin/`` mirrors the reference's
+own Python call surface (``optimizations``, ``RigidBodyPlanners.fcl_checker``,
+``scripts``).  The CUDA library is the only compute path: without ``libmst.so`` and a CUDA
+device every call raises.
+"""
+from . import _abi  # noqa: F401
+from .batch import (Mesh, PipelineResult, collide_poses, flat_outputs, formation_waypoints,  # noqa: F401
+                    pipeline, sample_batch, solve_batch, time_power_rows)
+
+__version__ = "0.1.0"
+
+
+def dropin_path() -> str:
+    """Directory to put in front of ``sys.path`` (or PYTHONPATH) so that
+    ``import optimizations`` / ``import RigidBodyPlanners`` resolve to the B200 drop-ins."""
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")

@@ -1,0 +1,248 @@
+"""Tensor-level API over libmst.so: the throughput path.
+
+Every function takes torch tensors (CUDA, or host tensors / numpy arrays which are copied
+to the current CUDA device), launches on ``torch.cuda.current_stream()`` and returns CUDA
+tensors.  PyTorch is only the allocator / stream provider here; all arithmetic happens in
+the hand-written kernels behind the C ABI (include/mst.h).  There is no CPU fallback.
+
+The legacy, object-per-trajectory surface of the reference (``optimizations``,
+``RigidBodyPlanners.fcl_checker``) lives in ``dropin/`` and is a thin adapter over this
+module.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi
+
+_SOLVERS = {"auto": _abi.SOLVER_AUTO, "banded_lu": _abi.SOLVER_BANDED_LU, "condensed": _abi.SOLVER_CONDENSED}
+_MODES = {"piecewise": _abi.SAMPLE_PIECEWISE, "trajectory": _abi.SAMPLE_TRAJECTORY}
+
+
+def _f64(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64)), device=device)
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------- a1
+def time_power_rows(t) -> torch.Tensor:
+    """``rows[count, 8, 8]``: derivative j, power k -> ``k!/(k-j)! * t**(k-j)``
+    (reference: Polynomial.pol_coeffs_at_t, src/optimizations/uav_trajectory.py:28-36)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    tt = _f64(t, dev).reshape(-1)
+    rows = torch.empty((tt.numel(), 8, 8), dtype=torch.float64, device=dev)
+    _abi.check(lib.mst_time_power_rows(_ptr(tt), tt.numel(), _ptr(rows), _stream_ptr()), "mst_time_power_rows")
+    return rows
+
+
+# --------------------------------------------------------------------------- a2-a4
+def solve_batch(wp, t, share_time_group: int = 1, solver: str = "auto"
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Minimum-snap solve of ``B`` trajectories.
+
+    wp ``[B, n+1, K]`` waypoints, t ``[B // share_time_group, n+1]`` time stamps.
+    Returns ``coef[B, n, K, 8]`` (ascending powers), ``dur[B, n]``, ``info[B]`` (int32;
+    0 ok, >0 singular at that column, <0 bad input — see include/mst.h).
+    Reference: calculate_trajectory1D/4D, src/optimizations/calculatingTrajectories.py:37-213.
+    """
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    wp = _f64(wp, dev)
+    t = _f64(t, dev)
+    if wp.dim() != 3 or t.dim() != 2:
+        raise ValueError("wp must be [B, n+1, K] and t [B/G, n+1]")
+    B, m, K = wp.shape
+    n = m - 1
+    G = int(share_time_group)
+    if n < 1:
+        raise IndexError("need at least two waypoints")  # the reference raises IndexError
+    if G < 1 or B % G != 0 or t.shape[0] != B // G or t.shape[1] != m:
+        raise ValueError("t must be [B/share_time_group, n+1]")
+    coef = torch.empty((B, n, K, 8), dtype=torch.float64, device=dev)
+    dur = torch.empty((B, n), dtype=torch.float64, device=dev)
+    info = torch.empty((B,), dtype=torch.int32, device=dev)
+    ws = torch.empty((max(1, lib.mst_solve_workspace_bytes(B, n, K, G)),), dtype=torch.uint8, device=dev)
+    rc = lib.mst_solve_batch(_ptr(wp), _ptr(t), B, n, K, G, _SOLVERS[solver], _ptr(coef), _ptr(dur),
+                             _ptr(info), _ptr(ws), _stream_ptr())
+    _abi.check(rc, "mst_solve_batch")
+    return coef, dur, info
+
+
+# --------------------------------------------------------------------------- a5/a6
+def sample_batch(coef, dur, ts=None, S: Optional[int] = None, mode: str = "piecewise", deriv: int = 0,
+                 return_status: bool = False):
+    """Evaluate ``coef[B, n, K, 8]`` / ``dur[B, n]`` at sample times.
+
+    ``ts`` may be ``[S]`` (shared), ``[B, S]`` (per trajectory) or None with ``S`` given
+    (uniform ``t_s = s * sum(dur)/S``).  Returns ``out[B, S, K]`` (+ ``status[B, S]``).
+    Reference: Polynomial.eval / PiecewisePolynomial.eval / Trajectory.eval,
+    src/optimizations/uav_trajectory.py:17-26,119-127,154-169.
+    """
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    coef = _f64(coef, dev)
+    dur = _f64(dur, dev)
+    B, n, K, _ = coef.shape
+    per = 0
+    if ts is None:
+        if S is None:
+            raise ValueError("give ts or S")
+        tsd = None
+    else:
+        tsd = _f64(ts, dev)
+        per = 1 if tsd.dim() == 2 else 0
+        S = tsd.shape[-1]
+        if per and tsd.shape[0] != B:
+            raise ValueError("per-trajectory ts must be [B, S]")
+    out = torch.empty((B, S, K), dtype=torch.float64, device=dev)
+    status = torch.empty((B, S), dtype=torch.uint8, device=dev)
+    rc = lib.mst_sample_batch(_ptr(coef), _ptr(dur), B, n, K, _ptr(tsd), per, S, _MODES[mode], int(deriv),
+                              _ptr(out), _ptr(status), _stream_ptr())
+    _abi.check(rc, "mst_sample_batch")
+    return (out, status) if return_status else out
+
+
+def flat_outputs(coef, dur, ts=None, S: Optional[int] = None, mode: str = "trajectory",
+                 return_status: bool = False):
+    """Differential-flatness outputs ``[B, S, 13] = pos vel acc omega yaw`` of 4-axis
+    trajectories (reference: Polynomial4D.eval, src/optimizations/uav_trajectory.py:66-101)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    coef = _f64(coef, dev)
+    dur = _f64(dur, dev)
+    B, n, K, _ = coef.shape
+    if K != 4:
+        raise ValueError("flat_outputs needs x, y, z, yaw (K = 4)")
+    per = 0
+    if ts is None:
+        if S is None:
+            raise ValueError("give ts or S")
+        tsd = None
+    else:
+        tsd = _f64(ts, dev)
+        per = 1 if tsd.dim() == 2 else 0
+        S = tsd.shape[-1]
+    out = torch.empty((B, S, 13), dtype=torch.float64, device=dev)
+    status = torch.empty((B, S), dtype=torch.uint8, device=dev)
+    rc = lib.mst_flat_outputs(_ptr(coef), _ptr(dur), B, n, _ptr(tsd), per, S, _MODES[mode], _ptr(out),
+                              _ptr(status), _stream_ptr())
+    _abi.check(rc, "mst_flat_outputs")
+    return (out, status) if return_status else out
+
+
+# --------------------------------------------------------------------------- a9
+def formation_waypoints(rb_poses, offsets, K: int = 4) -> torch.Tensor:
+    """``rb_poses[F, m, 4|7]`` x ``offsets[D, 3]`` -> ``wp[F*D, m, K]``
+    (reference: transform(path), scripts/drones_traj_generator.py:56-89)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    rb = _f64(rb_poses, dev)
+    off = _f64(offsets, dev)
+    F, m, pd = rb.shape
+    D = off.shape[0]
+    wp = torch.empty((F * D, m, K), dtype=torch.float64, device=dev)
+    rc = lib.mst_formation_waypoints(_ptr(rb), F, m, pd, _ptr(off), D, K, _ptr(wp), _stream_ptr())
+    _abi.check(rc, "mst_formation_waypoints")
+    return wp
+
+
+# --------------------------------------------------------------------------- a10-a12
+class Mesh:
+    """Device-resident triangle mesh (reference: Fcl_mesh,
+    src/RigidBodyPlanners/fcl_checker.py:13-59).  ``triangles`` is ``[T, 3, 3]`` float64,
+    already rounded the way ``load_stl`` rounds (see ``meshio.ingest_mesh``)."""
+
+    def __init__(self, triangles):
+        _abi.require_cuda()
+        lib = _abi.load()
+        tri = np.ascontiguousarray(np.asarray(triangles, dtype=np.float64).reshape(-1, 3, 3))
+        self.triangles = tri
+        handle = ctypes.c_void_p()
+        rc = lib.mst_mesh_create(tri.ctypes.data_as(ctypes.c_void_p), tri.shape[0], ctypes.byref(handle))
+        _abi.check(rc, "mst_mesh_create")
+        self._handle = handle
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def __len__(self):
+        return self.triangles.shape[0]
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            _abi.load().mst_mesh_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def collide_poses(robot: Mesh, env: Mesh, poses) -> torch.Tensor:
+    """``poses[P, 3|4|7]`` -> ``hit[P]`` uint8 (reference: Fcl_checker.check_collision via
+    isStateValid, fcl_checker.py:93-103, RB_planning_sep_coll_check.py:208-215)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    ps = _f64(poses, dev)
+    if ps.dim() != 2:
+        raise ValueError("poses must be [P, pose_dim]")
+    P, pd = ps.shape
+    hit = torch.empty((P,), dtype=torch.uint8, device=dev)
+    rc = lib.mst_collide_poses(robot.handle, env.handle, _ptr(ps), P, pd, _ptr(hit), _stream_ptr())
+    _abi.check(rc, "mst_collide_poses")
+    return hit
+
+
+# --------------------------------------------------------------------------- fused pipeline
+class PipelineResult:
+    __slots__ = ("coef", "dur", "info", "hit", "any_hit")
+
+    def __init__(self, coef, dur, info, hit, any_hit):
+        self.coef, self.dur, self.info, self.hit, self.any_hit = coef, dur, info, hit, any_hit
+
+
+def pipeline(wp, t, S: int, robot: Mesh, env: Mesh, share_time_group: int = 1, solver: str = "auto",
+             out: Optional[PipelineResult] = None) -> PipelineResult:
+    """Solve, sample ``S`` uniform times per trajectory, place the robot mesh at every
+    sample and collision-check it against ``env``.  Returns coefficients, durations,
+    solver status, ``hit[B, S]`` and ``any_hit[B]``."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    wp = _f64(wp, dev)
+    t = _f64(t, dev)
+    B, m, K = wp.shape
+    n = m - 1
+    G = int(share_time_group)
+    if n < 1:
+        raise IndexError("need at least two waypoints")
+    if G < 1 or B % G != 0 or t.shape[0] != B // G or t.shape[1] != m:
+        raise ValueError("t must be [B/share_time_group, n+1]")
+    if out is None:
+        out = PipelineResult(torch.empty((B, n, K, 8), dtype=torch.float64, device=dev),
+                             torch.empty((B, n), dtype=torch.float64, device=dev),
+                             torch.empty((B,), dtype=torch.int32, device=dev),
+                             torch.empty((B, S), dtype=torch.uint8, device=dev),
+                             torch.empty((B,), dtype=torch.uint8, device=dev))
+    ws = torch.empty((max(1, lib.mst_pipeline_workspace_bytes(B, n, K, G, S)),), dtype=torch.uint8, device=dev)
+    rc = lib.mst_pipeline(_ptr(wp), _ptr(t), B, n, K, G, _SOLVERS[solver], S, robot.handle, env.handle,
+                          _ptr(out.coef), _ptr(out.dur), _ptr(out.info), _ptr(out.hit), _ptr(out.any_hit),
+                          _ptr(ws), _stream_ptr())
+    _abi.check(rc, "mst_pipeline")
+    return out

@@ -1,0 +1,173 @@
+// extern "C" entry points of libmst.so (declared in include/mst.h).
+#include <stdio.h>
+#include <string.h>
+
+#include "mst_common.cuh"
+
+namespace mst {
+
+static thread_local char g_cuda_error[256] = "";
+
+void note_cuda_error(cudaError_t e) {
+  snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int check_launch() {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  return MST_OK;
+}
+
+// kernels' host launchers (one per .cu file)
+size_t banded_lu_smem_per_warp(int n, int R);
+int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K, int G, const int* list,
+                     const int* list_count, double* coef, double* dur, int* info, cudaStream_t stream);
+size_t condensed_workspace_bytes(int groups);
+int launch_condensed(const double* wp, const double* t, int groups, int n, int K, int G, int force,
+                     double* coef, double* dur, int* info, int* list, int* list_count,
+                     cudaStream_t stream);
+int launch_sample(const double* coef, const double* dur, int B, int n, int K, const double* ts,
+                  int ts_per_traj, int S, int mode, int deriv, double* out, uint8_t* status,
+                  cudaStream_t stream);
+int launch_flat(const double* coef, const double* dur, int B, int n, const double* ts, int ts_per_traj,
+                int S, int mode, double* out, uint8_t* status, cudaStream_t stream);
+int launch_time_power(const double* t, int count, double* rows, cudaStream_t stream);
+int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
+                   int pose_dim, uint8_t* hit, cudaStream_t stream);
+int launch_any_hit(const uint8_t* hit, int B, int S, uint8_t* any_hit, cudaStream_t stream);
+int launch_formation(const double* rb, int F, int m, int pose_dim, const double* off, int D, int K,
+                     double* wp, cudaStream_t stream);
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// trajectories per pass of the unfused pipeline: keeps the sampled positions
+// (chunk*S*K doubles) inside the 126 MB L2 instead of round-tripping through HBM
+static int pipeline_chunk(int B, int K, int S, int G) {
+  long long c = (96ll << 20) / ((long long)S * K * 8);
+  if (c < G) c = G;
+  c -= c % G;
+  if (c > B) c = B;
+  return (int)c;
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" int mst_version(void) { return MST_VERSION; }
+
+extern "C" const char* mst_strerror(int code) {
+  switch (code) {
+    case MST_OK: return "ok";
+    case MST_ERR_INVALID: return "invalid argument";
+    case MST_ERR_TOO_LARGE: return "problem does not fit the on-chip working set";
+    case MST_ERR_CUDA: return "CUDA runtime error";
+    case MST_ERR_NOMEM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* mst_last_cuda_error(void) { return g_cuda_error; }
+
+extern "C" int mst_time_power_rows(const double* t, int count, double* rows, void* stream) {
+  if (count < 0 || (count > 0 && (!t || !rows))) return MST_ERR_INVALID;
+  return launch_time_power(t, count, rows, (cudaStream_t)stream);
+}
+
+extern "C" size_t mst_solve_workspace_bytes(int B, int n, int K, int share_time_group) {
+  (void)n; (void)K;
+  if (B < 0 || share_time_group < 1) return 0;
+  return align256(condensed_workspace_bytes(B / share_time_group + 1));
+}
+
+extern "C" int mst_solve_batch(const double* wp, const double* t, int B, int n, int K,
+                               int share_time_group, int solver, double* coef, double* dur,
+                               int* info, void* workspace, void* stream) {
+  const int G = share_time_group;
+  if (B < 0 || n < 1 || K < 1 || G < 1 || B % G != 0) return MST_ERR_INVALID;
+  if (solver != MST_SOLVER_AUTO && solver != MST_SOLVER_BANDED_LU && solver != MST_SOLVER_CONDENSED)
+    return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
+  const int groups = B / G;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (banded_lu_smem_per_warp(n, G * K) > MST_MAX_SMEM && solver != MST_SOLVER_CONDENSED)
+    return MST_ERR_TOO_LARGE;
+  if (solver == MST_SOLVER_BANDED_LU)
+    return launch_banded_lu(wp, t, groups, n, K, G, nullptr, nullptr, coef, dur, info, st);
+  if (!workspace) return MST_ERR_INVALID;
+  int* list_count = (int*)workspace;
+  int* list = list_count + 64;
+  int rc = launch_condensed(wp, t, groups, n, K, G, solver == MST_SOLVER_CONDENSED, coef, dur, info,
+                            list, list_count, st);
+  if (rc != MST_OK || solver == MST_SOLVER_CONDENSED) return rc;
+  // groups the condensed path declined (duration spread too wide, t[0] != 0, bad input)
+  return launch_banded_lu(wp, t, groups, n, K, G, list, list_count, coef, dur, info, st);
+}
+
+extern "C" int mst_sample_batch(const double* coef, const double* dur, int B, int n, int K,
+                                const double* ts, int ts_per_traj, int S, int mode, int deriv,
+                                double* out, uint8_t* status, void* stream) {
+  if (B < 0 || n < 1 || K < 1 || S < 0 || deriv < 0 || deriv > 8) return MST_ERR_INVALID;
+  if (mode != MST_SAMPLE_PIECEWISE && mode != MST_SAMPLE_TRAJECTORY) return MST_ERR_INVALID;
+  if ((long long)B * S == 0) return MST_OK;
+  if (!coef || !dur || !out) return MST_ERR_INVALID;
+  return launch_sample(coef, dur, B, n, K, ts, ts_per_traj, S, mode, deriv, out, status,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int mst_flat_outputs(const double* coef, const double* dur, int B, int n, const double* ts,
+                                int ts_per_traj, int S, int mode, double* out, uint8_t* status,
+                                void* stream) {
+  if (B < 0 || n < 1 || S < 0) return MST_ERR_INVALID;
+  if (mode != MST_SAMPLE_PIECEWISE && mode != MST_SAMPLE_TRAJECTORY) return MST_ERR_INVALID;
+  if ((long long)B * S == 0) return MST_OK;
+  if (!coef || !dur || !out) return MST_ERR_INVALID;
+  return launch_flat(coef, dur, B, n, ts, ts_per_traj, S, mode, out, status, (cudaStream_t)stream);
+}
+
+extern "C" int mst_formation_waypoints(const double* rb, int F, int m, int pose_dim, const double* off,
+                                       int D, int K, double* wp, void* stream) {
+  if (F < 0 || m < 0 || D < 0 || (pose_dim != 4 && pose_dim != 7) || (K != 3 && K != 4))
+    return MST_ERR_INVALID;
+  if ((long long)F * m * D == 0) return MST_OK;
+  if (!rb || !off || !wp) return MST_ERR_INVALID;
+  return launch_formation(rb, F, m, pose_dim, off, D, K, wp, (cudaStream_t)stream);
+}
+
+extern "C" int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double* pose, int P,
+                                 int pose_dim, uint8_t* hit, void* stream) {
+  if (!robot || !env || P < 0 || (pose_dim != 3 && pose_dim != 4 && pose_dim != 7)) return MST_ERR_INVALID;
+  if (P == 0) return MST_OK;
+  if (!pose || !hit) return MST_ERR_INVALID;
+  return launch_collide(robot, env, pose, P, pose_dim, hit, (cudaStream_t)stream);
+}
+
+extern "C" size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_time_group, int S) {
+  if (B < 0 || S < 0 || K < 1 || share_time_group < 1) return 0;
+  const size_t solve = mst_solve_workspace_bytes(B, n, K, share_time_group);
+  const size_t chunk = (size_t)pipeline_chunk(B > 0 ? B : 1, K, S > 0 ? S : 1, share_time_group);
+  return solve + align256(chunk * (size_t)S * K * sizeof(double));
+}
+
+extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
+                            int share_time_group, int solver, int S, mst_mesh_t robot, mst_mesh_t env,
+                            double* coef, double* dur, int* info, uint8_t* hit, uint8_t* any_hit,
+                            void* workspace, void* stream) {
+  if (S < 1 || (K != 3 && K != 4) || !robot || !env) return MST_ERR_INVALID;
+  if (B > 0 && (!hit || !any_hit || !workspace)) return MST_ERR_INVALID;
+  int rc = mst_solve_batch(wp, t, B, n, K, share_time_group, solver, coef, dur, info, workspace, stream);
+  if (rc != MST_OK || B == 0) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* pos = (double*)((char*)workspace + mst_solve_workspace_bytes(B, n, K, share_time_group));
+  const int chunk = pipeline_chunk(B, K, S, share_time_group);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    rc = launch_sample(coef + (size_t)b0 * n * K * MST_NCOEF, dur + (size_t)b0 * n, nb, n, K, nullptr, 0,
+                       S, MST_SAMPLE_PIECEWISE, 0, pos, nullptr, st);
+    if (rc != MST_OK) return rc;
+    rc = launch_collide(robot, env, pos, (long long)nb * S, K, hit + (size_t)b0 * S, st);
+    if (rc != MST_OK) return rc;
+  }
+  return launch_any_hit(hit, B, S, any_hit, st);
+}

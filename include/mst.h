@@ -1,0 +1,184 @@
+/*
+ * mst.h — C ABI of libmst.so: batched minimum-snap trajectory generation, sampling,
+ * formation transform and mesh collision checking on NVIDIA B200 (sm_100a).
+ *
+ * The reference (mjmyt/drone_path_planning_python) is pure Python and has no FFI of
+ * its own; the drop-in boundary is its Python module surface.  The
+ * entry points below are what a binding for that surface calls — each one names the
+ * reference interface it replaces (paths relative to the reference checkout).  The
+ * Python side (drone_path_planning_python_b200/_abi.py) binds them with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every data pointer is a CUDA DEVICE pointer owned by the caller (e.g.
+ *    torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as void*
+ *    (0 = default stream).  Calls are asynchronous on that stream and re-entrant for
+ *    distinct streams / workspaces (rospy runs callback1/callback2 of
+ *    scripts/drones_pols_generator.py:22-37 on different threads).
+ *  - return value: MST_OK (0) or a negative MST_ERR_* code; nothing throws across
+ *    the ABI; no allocation happens after mst_mesh_create.
+ *  - all floating point is IEEE double.  Polynomial coefficients are in ASCENDING
+ *    power order, 8 per piece (7th order), as in the reference.
+ *  - layouts are row-major with the last index fastest.
+ */
+#ifndef MST_H_
+#define MST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MST_VERSION 100 /* 0.1.0 */
+
+enum {
+  MST_OK = 0,
+  MST_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, bad mode)     */
+  MST_ERR_TOO_LARGE = -2, /* problem does not fit the kernel's on-chip working set     */
+  MST_ERR_CUDA = -3,      /* a CUDA runtime call failed; see mst_last_cuda_error()     */
+  MST_ERR_NOMEM = -4      /* host or device allocation failed (mst_mesh_create only)   */
+};
+
+/* per-trajectory status written to info[] by the solvers */
+enum {
+  MST_INFO_OK = 0,            /* solved                                                  */
+  MST_INFO_DECREASING = -1,   /* a duration t[i+1]-t[i] (or t[0]) is negative: the
+                                 reference raises AssertionError
+                                 (src/optimizations/uav_trajectory.py:30)              */
+  MST_INFO_NONFINITE = -2,    /* NaN/Inf in times                                         */
+  MST_INFO_DECLINED = -3      /* MST_SOLVER_CONDENSED was forced on a group it cannot
+                                 reproduce (t[0] != 0)              */
+  /* > 0: zero pivot met at column info (1-based): the reference raises
+     numpy.linalg.LinAlgError("Singular matrix")
+     (src/optimizations/calculatingTrajectories.py:137)                                  */
+};
+
+/* solver selection for mst_solve_batch / mst_pipeline */
+enum {
+  MST_SOLVER_AUTO = 0,   /* condensed LDL^T where the duration spread allows it, banded
+                            LU with partial pivoting otherwise (decided per time group) */
+  MST_SOLVER_BANDED_LU = 1,
+  MST_SOLVER_CONDENSED = 2
+};
+
+/* piece selection semantics for mst_sample_batch */
+enum {
+  MST_SAMPLE_PIECEWISE = 0, /* PiecewisePolynomial.eval: strict t < acc+T_i, extrapolates
+                               the last piece (src/optimizations/uav_trajectory.py:154-169) */
+  MST_SAMPLE_TRAJECTORY = 1 /* Trajectory.eval: inclusive t <= acc+T_i
+                               (src/optimizations/uav_trajectory.py:119-127)              */
+};
+
+int mst_version(void);
+const char* mst_strerror(int code);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* mst_last_cuda_error(void);
+
+/*
+ * Time-power rows — Polynomial.pol_coeffs_at_t applied to the j-th derivative of the
+ * all-ones polynomial and left-padded to 8 (src/optimizations/uav_trajectory.py:25-36,
+ * src/optimizations/calculatingTrajectories.py:68-71,93-97,105-109).
+ *   t[count]            -> rows[count][8 (derivative j)][8 (power k)] = k!/(k-j)! * t^(k-j)
+ */
+int mst_time_power_rows(const double* t, int count, double* rows, void* stream);
+
+/*
+ * Batched minimum-snap solve — calculate_trajectory1D / calculate_trajectory4D
+ * (src/optimizations/calculatingTrajectories.py:37-213): for every trajectory the
+ * 8n x 8n interpolation + C^1..C^6 continuity + rest-to-rest system is solved for
+ * all K axes at once.
+ *   wp   [B][n+1][K]   waypoint values per axis (x, y, z[, yaw])
+ *   t    [B/G][n+1]    time stamps; G = share_time_group consecutive trajectories use
+ *                      the same stamps (the D drones of a formation inherit the rigid
+ *                      body path's stamps, scripts/drones_pols_generator.py:44-56);
+ *                      G = 1 gives every trajectory its own stamps.  B % G must be 0.
+ *   coef [B][n][K][8]  piece-major: one row of the reference's Pol_matrix per piece
+ *   dur  [B][n]        durations T_i = t[i+1]-t[i]  (PiecewisePolynomial.time_durations)
+ *   info [B]           MST_INFO_* per trajectory
+ *   workspace          mst_solve_workspace_bytes(B, n, K, G) bytes of device scratch
+ */
+size_t mst_solve_workspace_bytes(int B, int n, int K, int share_time_group);
+int mst_solve_batch(const double* wp, const double* t, int B, int n, int K,
+                    int share_time_group, int solver, double* coef, double* dur,
+                    int* info, void* workspace, void* stream);
+
+/*
+ * Batched evaluation — Polynomial.eval / Polynomial.derivative /
+ * PiecewisePolynomial.eval / Trajectory.eval
+ * (src/optimizations/uav_trajectory.py:17-26,119-127,154-169).
+ *   coef [B][n][K][8], dur [B][n]
+ *   ts   [S] (ts_per_traj = 0), [B][S] (ts_per_traj = 1), or NULL: uniform
+ *        t_s = s * (sum(dur)/S), the np.arange(0, duration, step) pattern of
+ *        src/trajectory_visualising/visualization.py:53
+ *   mode MST_SAMPLE_*; deriv 0..7 (Polynomial.derivative applied `deriv` times)
+ *   out  [B][S][K]; status [B][S] (may be NULL): 0 ok, 1 = t violates the
+ *        reference's assert (t < 0, or t > duration in TRAJECTORY mode) -> out = NaN
+ */
+int mst_sample_batch(const double* coef, const double* dur, int B, int n, int K,
+                     const double* ts, int ts_per_traj, int S, int mode, int deriv,
+                     double* out, uint8_t* status, void* stream);
+
+/*
+ * Differential-flatness outputs — Polynomial4D.eval through Trajectory.eval
+ * (src/optimizations/uav_trajectory.py:66-101,119-127); K must be 4.
+ *   out [B][S][13] = pos(3) vel(3) acc(3) omega(3) yaw(1)
+ */
+int mst_flat_outputs(const double* coef, const double* dur, int B, int n,
+                     const double* ts, int ts_per_traj, int S, int mode,
+                     double* out, uint8_t* status, void* stream);
+
+/*
+ * Formation rigid-body transform — transform(path) of
+ * scripts/drones_traj_generator.py:56-89: p_d = R(q_rb) * offset_d + t_rb, the rigid
+ * body's heading carried over to every drone.
+ *   rb   [F][m][pose_dim]  pose_dim 4: (x,y,z,yaw); 7: (x,y,z,qx,qy,qz,qw)
+ *   off  [D][3]
+ *   wp   [F*D][m][K]       K = 3 (position) or 4 (position + yaw); trajectory index
+ *                          f*D + d, ready for mst_solve_batch(share_time_group = D)
+ */
+int mst_formation_waypoints(const double* rb, int F, int m, int pose_dim,
+                            const double* off, int D, int K, double* wp, void* stream);
+
+/*
+ * Triangle meshes — Fcl_mesh (src/RigidBodyPlanners/fcl_checker.py:13-59).  `tri` is a
+ * HOST pointer to [T][3][3] doubles (already rounded to 2 decimals by the caller as
+ * load_stl does, :20-23); the mesh (triangles, per-triangle AABBs, root AABB) is
+ * copied to the current CUDA device.
+ */
+typedef struct mst_mesh* mst_mesh_t;
+int mst_mesh_create(const double* tri, int T, mst_mesh_t* out);
+int mst_mesh_destroy(mst_mesh_t mesh);
+int mst_mesh_triangle_count(mst_mesh_t mesh);
+
+/*
+ * Batched collision query — Fcl_checker.set_robot_transform + check_collision
+ * (src/RigidBodyPlanners/fcl_checker.py:93-103) as called by isStateValid
+ * (src/RigidBodyPlanners/RB_planning_sep_coll_check.py:208-215): robot mesh at each
+ * pose against the environment mesh at identity; hit = 1 iff some triangle pair
+ * intersects (touching counts).
+ *   pose [P][pose_dim]  pose_dim 4: (x,y,z,yaw) or 7: (x,y,z,qx,qy,qz,qw)
+ *   hit  [P]
+ */
+int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double* pose, int P,
+                      int pose_dim, uint8_t* hit, void* stream);
+
+/*
+ * Fused pipeline: solve -> sample S uniform times -> place the robot mesh at every
+ * sampled position (yaw = sampled 4th axis when K = 4, else 0) -> collide.
+ *   inputs / coef / dur / info as mst_solve_batch
+ *   hit     [B][S]  per-sample collision flag
+ *   any_hit [B]     1 iff any sample of the trajectory collides
+ *   workspace       mst_pipeline_workspace_bytes(B, n, K, G, S) bytes
+ */
+size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_time_group, int S);
+int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
+                 int share_time_group, int solver, int S, mst_mesh_t robot,
+                 mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,
+                 uint8_t* any_hit, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MST_H_ */

@@ -1,0 +1,127 @@
+"""GPU parity tests for the collision half and the fused pipeline.
+
+The oracle is a restatement of FCL's published mesh-mesh test (parity UNPINNED: FCL is not
+in the reference tree — see oracle/collision_oracle.py).  Flags must be bit-exact except for
+poses whose margin to the touching boundary is below EPS (north star).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EPS = 1e-9
+BOUNDS_LO = np.array([-2.2, 2.8, 0.5])   # RB_planning_sep_coll_check.py:102-110
+BOUNDS_HI = np.array([2.2, 5.0, 2.5])
+
+
+def _soup(name):
+    from drone_path_planning_python_b200 import meshio
+    verts, _, tris = meshio.ingest_mesh(meshio.shipped_mesh(name))
+    return meshio.triangle_soup(verts, tris)
+
+
+def _random_poses(rng, P, dim):
+    pos = rng.uniform(BOUNDS_LO - 0.5, BOUNDS_HI + 0.5, (P, 3))
+    if dim == 3:
+        return pos
+    yaw = rng.uniform(-np.pi, np.pi, P)
+    if dim == 4:
+        return np.concatenate([pos, yaw[:, None]], axis=1)
+    q = rng.normal(size=(P, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return np.concatenate([pos, q], axis=1)
+
+
+@pytest.mark.parametrize("env_name", ["env-scene-ltu-experiment", "env-scene-narrow", "env-scene-hole"])
+@pytest.mark.parametrize("dim", [4, 7])
+def test_collide_poses_vs_oracle(env_name, dim):
+    from oracle import collision_oracle as co
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(sum(env_name.encode()) * 10 + dim)
+    robot_tris, env_tris = _soup("custom_triangle_robot"), _soup(env_name)
+    robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
+    P = 3000 if len(env_tris) > 24 else 6000
+    poses = _random_poses(rng, P, dim)
+    hit = mst.collide_poses(robot, env, poses).cpu().numpy()
+    ref, margin = co.collide_poses(robot_tris, env_tris, poses, with_margin=True)
+    clear = np.abs(margin) > EPS
+    assert clear.mean() > 0.99
+    assert np.array_equal(hit[clear], ref[clear])
+    assert 0.02 < ref.mean() < 0.9     # both outcomes are exercised
+
+
+def test_collide_translation_only_and_degenerate_robot():
+    from oracle import collision_oracle as co
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(3)
+    robot_tris = _soup("robot-scene-triangle")      # has 4 zero-area facets
+    env_tris = _soup("env-scene-ltu-experiment")
+    robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
+    pos = _random_poses(rng, 4000, 3)
+    hit = mst.collide_poses(robot, env, pos).cpu().numpy()
+    ref, margin = co.collide_poses(robot_tris, env_tris, np.concatenate([pos, np.zeros((4000, 1))], 1),
+                                   with_margin=True)
+    clear = np.abs(margin) > EPS
+    assert np.array_equal(hit[clear], ref[clear])
+
+
+def test_known_answers_live_pair():
+    """Weak anchors from SURVEY §8c: the wall of env-scene-ltu-experiment spans
+    x in [-2,2], y in [3.9,4.1], z in [0,1.6]; a robot centred in it straddles both faces;
+    the planner's start/goal states and a pass well above the wall are free."""
+    import drone_path_planning_python_b200 as mst
+    robot, env = mst.Mesh(_soup("custom_triangle_robot")), mst.Mesh(_soup("env-scene-ltu-experiment"))
+    poses = np.array([[0.0, 4.0, 1.0, 0.0],     # inside the wall -> collision
+                      [0.0, 4.0, 1.0, 1.2],
+                      [0.0, 3.0, 1.0, 0.0],     # planner start (scripts/rigidBodyPath.py:146)
+                      [0.0, 5.0, 1.0, 0.0],     # planner goal  (:147)
+                      [0.0, 4.0, 2.17, 0.3]])   # over the wall, as the shipped path does
+    hit = mst.collide_poses(robot, env, poses).cpu().numpy()
+    assert hit.tolist() == [1, 1, 0, 0, 0]
+
+
+def test_pipeline_equals_separate_stages():
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(9)
+    robot, env = mst.Mesh(_soup("custom_triangle_robot")), mst.Mesh(_soup("env-scene-ltu-experiment"))
+    for K in (3, 4):
+        B, n, S = 300, 10, 100
+        T = rng.uniform(0.5, 2.0, (B, n))
+        t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+        start = rng.uniform(BOUNDS_LO, BOUNDS_HI, (B, 1, 3))
+        wp = np.zeros((B, n + 1, K))
+        wp[:, :, :3] = start + np.cumsum(rng.normal(0, 0.3, (B, n + 1, 3)), axis=1)
+        if K == 4:
+            wp[:, :, 3] = np.cumsum(rng.normal(0, 0.1, (B, n + 1)), axis=1)
+        res = mst.pipeline(wp, t, S, robot, env)
+        coef, dur, info = mst.solve_batch(wp, t)
+        assert np.array_equal(res.coef.cpu().numpy(), coef.cpu().numpy())
+        assert np.array_equal(res.info.cpu().numpy(), info.cpu().numpy())
+        pos = mst.sample_batch(coef, dur, S=S)
+        hit = mst.collide_poses(robot, env, pos.reshape(B * S, K)).reshape(B, S)
+        assert np.array_equal(res.hit.cpu().numpy(), hit.cpu().numpy())
+        assert np.array_equal(res.any_hit.cpu().numpy(), hit.cpu().numpy().max(axis=1))
+        assert 0 < res.any_hit.float().mean() < 1
+
+
+def test_pipeline_samples_match_oracle_end_to_end():
+    from oracle import collision_oracle as co
+    from oracle import minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(21)
+    robot_tris, env_tris = _soup("custom_triangle_robot"), _soup("env-scene-ltu-experiment")
+    robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
+    B, n, K, S = 24, 10, 3, 100
+    T = rng.uniform(0.5, 2.0, (B, n))
+    t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+    wp = rng.uniform(BOUNDS_LO, BOUNDS_HI, (B, 1, 3)) + np.cumsum(rng.normal(0, 0.3, (B, n + 1, 3)), axis=1)
+    res = mst.pipeline(wp, t, S, robot, env)
+    hit = res.hit.cpu().numpy()
+    for b in range(B):
+        coef, dur = mo.solve_waypoints(wp[b], t[b])
+        ts = mo.uniform_sample_times(dur, S)
+        pos = mo.sample_trajectory(coef, dur, ts)
+        ref, margin = co.collide_poses(robot_tris, env_tris, np.concatenate([pos, np.zeros((S, 1))], 1),
+                                       with_margin=True)
+        clear = np.abs(margin) > 1e-7     # positions themselves carry ~1e-12 solver differences
+        assert np.array_equal(hit[b][clear], ref[clear]), b

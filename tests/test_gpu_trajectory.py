@@ -1,0 +1,221 @@
+"""GPU parity tests for the trajectory half: CUDA path, called through the
+C ABI (ctypes), against the committed reference outputs (tests/golden, produced by the
+unmodified reference — oracle/make_golden.py) and against the oracle on seeded inputs.
+
+Tolerances (north star): coefficients  max|c - c_ref| <= 1e-9 * max|c_ref| per (trajectory,
+axis); sampled values |x - x_ref| <= 1e-9 * max(1, |x_ref|).  Evaluation of given
+coefficients is bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+COEF_TOL = 1e-9
+
+
+def _load(golden_dir, name):
+    with np.load(os.path.join(golden_dir, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _cases(golden_dir):
+    z = _load(golden_dir, "solve_cases.npz")
+    names = sorted({k.split("__")[0] for k in z})
+    return [(nm, z[nm + "__wp"], z[nm + "__t"], z[nm + "__coef"], z[nm + "__dur"]) for nm in names]
+
+
+def normwise(c, ref):
+    """max over axes of max|c-ref| / max|ref|; arrays [n, K, 8]."""
+    num = np.abs(c - ref).max(axis=(0, 2))
+    den = np.abs(ref).max(axis=(0, 2))
+    return float((num / den).max())
+
+
+def test_time_power_rows_bit_exact(golden_dir):
+    import drone_path_planning_python_b200 as mst
+    z = _load(golden_dir, "time_power_rows.npz")
+    rows = mst.time_power_rows(z["t"]).cpu().numpy()
+    assert np.array_equal(rows, z["rows"])
+
+
+@pytest.mark.parametrize("solver", ["banded_lu", "auto"])
+def test_solve_matches_reference_goldens(golden_dir, solver):
+    import drone_path_planning_python_b200 as mst
+    worst = 0.0
+    for name, wp, t, coef_ref, dur_ref in _cases(golden_dir):
+        coef, dur, info = mst.solve_batch(wp[None], t[None], solver=solver)
+        assert int(info[0]) == 0, name
+        assert np.array_equal(dur[0].cpu().numpy(), dur_ref), name
+        err = normwise(coef[0].cpu().numpy(), coef_ref)
+        worst = max(worst, err)
+        assert err <= COEF_TOL, (name, solver, err)
+    print("worst normwise coefficient error (%s): %.2e" % (solver, worst))
+
+
+def test_condensed_forced_on_benign_goldens(golden_dir):
+    import drone_path_planning_python_b200 as mst
+    for name, wp, t, coef_ref, _ in _cases(golden_dir):
+        if not (name.startswith("rand") or name.startswith("uniform") or name.startswith("reference")):
+            continue
+        coef, _, info = mst.solve_batch(wp[None], t[None], solver="condensed")
+        assert int(info[0]) == 0, name
+        assert normwise(coef[0].cpu().numpy(), coef_ref) <= COEF_TOL, name
+
+
+def test_condensed_declines_t0_quirk(golden_dir):
+    import drone_path_planning_python_b200 as mst
+    z = _load(golden_dir, "solve_cases.npz")
+    _, _, info = mst.solve_batch(z["t0_nonzero_n6__wp"][None], z["t0_nonzero_n6__t"][None], solver="condensed")
+    assert int(info[0]) == -3
+
+
+@pytest.mark.parametrize("n,K,B", [(1, 3, 33), (2, 4, 33), (10, 3, 257), (10, 4, 64), (20, 3, 64), (49, 4, 8)])
+def test_solve_batch_vs_oracle_seeded(n, K, B):
+    from oracle import minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(1000 + 10 * n + K)
+    T = rng.uniform(0.5, 2.0, (B, n))
+    t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+    wp = np.cumsum(rng.normal(0, 0.3, (B, n + 1, K)), axis=1) + rng.uniform(-2, 2, (B, 1, K))
+    outs = {s: mst.solve_batch(wp, t, solver=s) for s in ("banded_lu", "condensed", "auto")}
+    check = range(B) if n <= 20 else range(min(B, 4))
+    for b in check:
+        ref, dref = mo.solve_waypoints(wp[b], t[b])
+        for s, (coef, dur, info) in outs.items():
+            assert int(info[b]) == 0
+            assert np.array_equal(dur[b].cpu().numpy(), dref)
+            assert normwise(coef[b].cpu().numpy(), ref) <= COEF_TOL, (s, b)
+    # auto == condensed here (spread < 4): identical bits
+    assert np.array_equal(outs["auto"][0].cpu().numpy(), outs["condensed"][0].cpu().numpy())
+
+
+def test_auto_routes_wide_spreads_to_pivoted_solver():
+    from oracle import minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(77)
+    B, n, K = 96, 20, 3
+    T = np.clip(rng.uniform(0.5, 2.0, (B, n)) * np.exp(rng.normal(0, 1.0, (B, n))), 0.05, 5.0)
+    T[::3] = rng.uniform(0.5, 2.0, (B // 3, n))  # a third stays benign
+    t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+    wp = np.cumsum(rng.normal(0, 0.3, (B, n + 1, K)), axis=1)
+    coef, dur, info = mst.solve_batch(wp, t, solver="auto")
+    lu, _, _ = mst.solve_batch(wp, t, solver="banded_lu")
+    coef, lu = coef.cpu().numpy(), lu.cpu().numpy()
+    assert (info.cpu().numpy() == 0).all()
+    spread = T.max(axis=1) / T.min(axis=1)
+    wide = spread > 4.0
+    assert wide.any() and (~wide).any()
+    assert np.array_equal(coef[wide], lu[wide])  # the very same kernel produced them
+    for b in range(0, B, 5):
+        ref, _ = mo.solve_waypoints(wp[b], t[b])
+        assert normwise(coef[b], ref) <= COEF_TOL, (b, spread[b])
+
+
+def test_shared_time_group_formation():
+    from oracle import minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(5)
+    F, D, n, K = 7, 5, 10, 3
+    offsets = np.array([[0.5, 0, 0], [-0.5, 0, 0], [0, 0, -0.5], [0, 0.5, 0], [0, -0.5, 0]])
+    rb = np.zeros((F, n + 1, 4))
+    rb[:, :, :3] = np.cumsum(rng.normal(0, 0.3, (F, n + 1, 3)), axis=1) + [0, 4, 1.5]
+    rb[:, :, 3] = np.cumsum(rng.normal(0, 0.1, (F, n + 1)), axis=1)
+    T = rng.uniform(0.5, 2.0, (F, n))
+    t = np.concatenate([np.zeros((F, 1)), np.cumsum(T, axis=1)], axis=1)
+    wp = mst.formation_waypoints(rb, offsets, K=K)
+    assert wp.shape == (F * D, n + 1, K)
+    wp_np = wp.cpu().numpy()
+    for f in range(F):
+        ref = mo.formation_waypoints(rb[f], offsets)
+        assert np.allclose(wp_np[f * D:(f + 1) * D], ref[:, :, :K], rtol=0, atol=1e-14)
+    for solver in ("auto", "banded_lu"):
+        coef, dur, info = mst.solve_batch(wp, t, share_time_group=D, solver=solver)
+        assert (info.cpu().numpy() == 0).all()
+        for f in (0, F - 1):
+            for d in range(D):
+                ref, dref = mo.solve_waypoints(wp_np[f * D + d], t[f])
+                assert np.array_equal(dur[f * D + d].cpu().numpy(), dref)
+                assert normwise(coef[f * D + d].cpu().numpy(), ref) <= COEF_TOL
+
+
+def test_error_reporting_matches_reference_failures():
+    import drone_path_planning_python_b200 as mst
+    wp = np.zeros((3, 4, 3))
+    t = np.array([[0.0, 1.0, 1.0, 2.0],      # equal consecutive times -> singular (LinAlgError)
+                  [0.0, 1.0, 0.5, 2.0],      # decreasing -> AssertionError in the reference
+                  [0.0, np.nan, 1.0, 2.0]])
+    for solver in ("auto", "banded_lu", "condensed"):
+        coef, _, info = mst.solve_batch(wp, t, solver=solver)
+        info = info.cpu().numpy()
+        assert info[0] > 0 and info[1] == -1 and info[2] == -2, (solver, info)
+        assert np.isnan(coef[1].cpu().numpy()).all()
+    with pytest.raises(IndexError):
+        mst.solve_batch(np.zeros((1, 1, 3)), np.zeros((1, 1)))
+
+
+def test_piecewise_eval_bit_exact(golden_dir):
+    import drone_path_planning_python_b200 as mst
+    z = _load(golden_dir, "piecewise_eval.npz")
+    coef, dur, ts = z["coef"][None], z["dur"][None], z["t"]
+    out = mst.sample_batch(coef, dur, ts=ts).cpu().numpy()[0]
+    inside = ts < dur.sum() - 1e-9   # past the end Python's sum() is compensated: allow an ulp-level difference
+    assert np.array_equal(out[inside], z["values"][inside])
+    assert np.allclose(out, z["values"], rtol=1e-12, atol=0)
+    for level in (1, 2, 3):
+        d = mst.sample_batch(coef, dur, ts=ts, deriv=level).cpu().numpy()[0]
+        assert np.array_equal(d[inside], z["deriv_values"][level - 1][inside])
+    # negative time: the reference asserts
+    _, status = mst.sample_batch(coef, dur, ts=np.array([-0.1, 0.0]), return_status=True)
+    assert status.cpu().numpy().tolist() == [[1, 0]]
+
+
+def test_trajectory_eval_and_flat_outputs(golden_dir):
+    import drone_path_planning_python_b200 as mst
+    z = _load(golden_dir, "trajectory_eval.npz")
+    for label in ("traj", "pol1"):
+        rows = z[label + "__file_rows"]
+        used = rows if label == "traj" else rows[1:]      # loadcsv skips the first line
+        assert used.shape[0] == int(z[label + "__n_pieces"])
+        coef = used[:, 1:].reshape(1, -1, 4, 8)
+        dur = used[:, 0][None]
+        ts = z[label + "__t"]
+        out, status = mst.flat_outputs(coef, dur, ts=ts, mode="trajectory", return_status=True)
+        out = out.cpu().numpy()[0]
+        assert (status.cpu().numpy() == 0).all()
+        assert np.array_equal(out[:, 0:3], z[label + "__pos"])
+        assert np.array_equal(out[:, 3:6], z[label + "__vel"])
+        assert np.array_equal(out[:, 6:9], z[label + "__acc"])
+        assert np.array_equal(out[:, 12], z[label + "__yaw"])
+        assert np.allclose(out[:, 9:12], z[label + "__omega"], rtol=1e-11, atol=1e-13)
+        # Trajectory.eval asserts t <= duration
+        _, st = mst.flat_outputs(coef, dur, ts=np.array([float(dur.sum()) + 1e-6]), return_status=True)
+        assert int(st[0, 0]) == 1
+
+
+def test_shipped_pol_matrices_reproduce_in_position_space(golden_dir):
+    """re-solve from the waypoints recoverable out of the shipped CSVs and
+    compare sampled positions (the CSVs are float32; coefficient space is ill-posed)."""
+    from oracle import minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    z = _load(golden_dir, "shipped_pol_matrices.npz")
+    for name in ("Pol_matrix_1", "Pol_matrix_2", "Pol_matrix_1_simple", "Pol_matrix_2_simple"):
+        mat = z[name].astype(np.float64)
+        n = mat.shape[0]
+        c = mat[:, 1:].reshape(n, 4, 8)
+        T = mat[:, 0]
+        wps = np.zeros((n + 1, 4))
+        wps[:n] = c[:, :, 0]
+        wps[n] = [mo.horner(c[n - 1, k], T[n - 1]) for k in range(4)]
+        t = mo.uniform_times(n + 1)
+        for solver in ("auto", "banded_lu"):
+            coef, dur, info = mst.solve_batch(wps[None], t[None], solver=solver)
+            assert int(info[0]) == 0
+            packed = mo.pack_pol_matrix(coef[0].cpu().numpy(), dur[0].cpu().numpy())
+            ts = np.linspace(0, float(T.sum()) * 0.999, 200)
+            ours = mst.sample_batch(packed[None, :, 1:].reshape(1, n, 4, 8).astype(np.float64),
+                                    packed[None, :, 0].astype(np.float64), ts=ts).cpu().numpy()[0]
+            theirs = mst.sample_batch(c[None], T[None], ts=ts).cpu().numpy()[0]
+            assert np.abs(ours[:, :3] - theirs[:, :3]).max() < 1e-6, (name, solver)
