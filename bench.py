@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: min-snap solve + sample + collision check (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+One *step* = one pass of the whole pipeline over the per-GPU batch.  Workload (BASELINE.json
+configs[4], the one the metric is quoted on): 1,048,576 independent trajectories per GPU x 10
+pieces x 3 axes, one time vector per trajectory (T_i ~ U(0.5, 2) s), S = 100 samples each,
+robot `custom_triangle_robot` vs obstacle `env-scene-ltu-experiment`, seed 20261019 (SURVEY
+§8d).  Inputs + outputs are ~2.4 GB per step, far larger than the 126 MB L2.
+
+Multi-GPU (torchrun, one process per GPU): trajectories are sharded by index, every rank
+runs the same per-GPU batch (weak scaling), and the final coefficients and collision flags
+are all-gathered over NCCL, chunk by chunk, overlapped with the next chunk's kernels.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SEG, K_AX, S_SAMPLES = 10, 3, 100
+TRAJ_PER_GPU = 1 << 20
+SEED = 20261019
+ROBOT, ENV = "custom_triangle_robot", "env-scene-ltu-experiment"
+METRIC = "min-snap trajectories solved+collision-checked per second"
+UNIT = "trajectories/s"
+# compulsory HBM bytes per trajectory: waypoints + stamps in, coefficients +
+# per-sample flags + any-flag out (durations and solver status are extra outputs we also write)
+ALG_BYTES = (N_SEG + 1) * K_AX * 8 + (N_SEG + 1) * 8 + N_SEG * K_AX * 64 + S_SAMPLES + 1
+BOUNDS_LO = np.array([-2.2, 2.8, 0.5])
+BOUNDS_HI = np.array([2.2, 5.0, 2.5])
+
+
+def make_workload(B, seed):
+    """Config-5 generator: start uniform in the OMPL bounds, steps N(0, 0.3^2)."""
+    rng = np.random.default_rng(seed)
+    T = rng.uniform(0.5, 2.0, (B, N_SEG))
+    t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+    wp = rng.normal(0.0, 0.3, (B, N_SEG + 1, K_AX))
+    wp[:, 0, :] = rng.uniform(BOUNDS_LO, BOUNDS_HI, (B, K_AX))
+    np.cumsum(wp, axis=1, out=wp)
+    return wp, t
+
+
+def mesh_soups():
+    from drone_path_planning_python_b200 import meshio
+    out = []
+    for name in (ROBOT, ENV):
+        verts, _, tris = meshio.ingest_mesh(meshio.shipped_mesh(name))
+        out.append(meshio.triangle_soup(verts, tris))
+    return out
+
+
+# --------------------------------------------------------------------------- CPU arm
+_CPU_STATE = {}
+
+
+def _cpu_init():
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    from oracle import build_oracle  # noqa: F401
+    _CPU_STATE["soups"] = mesh_soups()
+
+
+def _cpu_work(args):
+    """Reference algorithm for a slice of trajectories: per-axis dense assembly + solve,
+    Python Horner sampling (oracle/minsnap_oracle.py), C SAT collision (oracle/collision_oracle.c)."""
+    from oracle import build_oracle, minsnap_oracle as mo
+    wp, t = args
+    robot, env = _CPU_STATE["soups"]
+    hits = 0
+    for b in range(wp.shape[0]):
+        coef, dur = mo.solve_waypoints(wp[b], t[b])
+        ts = mo.uniform_sample_times(dur, S_SAMPLES)
+        pos = mo.sample_trajectory(coef, dur, ts)
+        poses = np.concatenate([pos, np.zeros((S_SAMPLES, 1))], axis=1)
+        hits += int(build_oracle.c_collide_poses(robot, env, poses).any())
+    return hits
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuArm:
+    def __init__(self, cores):
+        import multiprocessing as mp
+        from oracle import build_oracle
+        build_oracle.build()
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init)
+
+    def run(self, wp, t):
+        parts = np.array_split(np.arange(wp.shape[0]), self.cores)
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_work, [(wp[p], t[p]) for p in parts if len(p)])
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_step = 16 * cores
+    wp, t = make_workload(per_step * (args.steps + args.warmup), SEED)
+    arm = CpuArm(cores)
+    for w in range(args.warmup):
+        sl = slice(w * per_step, (w + 1) * per_step)
+        arm.run(wp[sl], t[sl])
+    elapsed = 0.0
+    for s in range(args.steps):
+        sl = slice((args.warmup + s) * per_step, (args.warmup + s + 1) * per_step)
+        elapsed += arm.run(wp[sl], t[sl])
+    arm.close()
+    value = per_step * args.steps / elapsed
+    sample = "%d trajectories per step (16 per core) of the same generator" % per_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4] shape: %d pieces x %d axes, S=%d, %s vs %s; bounded sample"
+                               % (N_SEG, K_AX, S_SAMPLES, ROBOT, ENV), "trajectories_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import drone_path_planning_python_b200 as mst
+    from drone_path_planning_python_b200 import _abi
+    from drone_path_planning_python_b200.host_pipeline import HostPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _abi.load()
+    B = args.traj
+    robot_soup, env_soup = mesh_soups()
+    robot, env = mst.Mesh(robot_soup), mst.Mesh(env_soup)
+    wp_np, t_np = make_workload(B, SEED + rank)
+    wp_host = torch.from_numpy(wp_np).pin_memory()
+    t_host = torch.from_numpy(t_np).pin_memory()
+    wp = wp_host.to(dev)
+    t = t_host.to(dev)
+
+    res = mst.PipelineResult(torch.empty((B, N_SEG, K_AX, 8), dtype=torch.float64, device=dev),
+                             torch.empty((B, N_SEG), dtype=torch.float64, device=dev),
+                             torch.empty((B,), dtype=torch.int32, device=dev),
+                             torch.empty((B, S_SAMPLES), dtype=torch.uint8, device=dev),
+                             torch.empty((B,), dtype=torch.uint8, device=dev))
+
+    # multi-GPU: chunked all-gather of coefficients + flags, overlapped with the next chunk
+    n_chunks = args.gather_chunks if world > 1 else 1
+    cb = B // n_chunks
+    gathered = None
+    if world > 1:
+        gathered = [(torch.empty((world, cb, N_SEG, K_AX, 8), dtype=torch.float64, device=dev),
+                     torch.empty((world, cb, S_SAMPLES), dtype=torch.uint8, device=dev),
+                     torch.empty((world, cb), dtype=torch.uint8, device=dev)) for _ in range(n_chunks)]
+
+    def step():
+        if world == 1:
+            mst.pipeline(wp, t, S_SAMPLES, robot, env, out=res)
+            return
+        handles = []
+        for c in range(n_chunks):
+            sl = slice(c * cb, (c + 1) * cb)
+            view = mst.PipelineResult(res.coef[sl], res.dur[sl], res.info[sl], res.hit[sl], res.any_hit[sl])
+            mst.pipeline(wp[sl], t[sl], S_SAMPLES, robot, env, out=view)
+            g = gathered[c]
+            handles.append(dist.all_gather_into_tensor(g[0], view.coef, async_op=True))
+            handles.append(dist.all_gather_into_tensor(g[1], view.hit, async_op=True))
+            handles.append(dist.all_gather_into_tensor(g[2], view.any_hit, async_op=True))
+        for h in handles:
+            h.wait()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms = timed(step, args.steps)
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    bad = int((res.info != 0).sum().item())
+    hit_rate = float(res.any_hit.float().mean().item())
+
+    # --- dominant kernel alone, timed live with CUDA events on the launching stream ------
+    stage_ms = {}
+    coef_d, dur_d, info_d = res.coef, res.dur, res.info
+    ws = torch.empty((max(1, lib.mst_solve_workspace_bytes(B, N_SEG, K_AX, 1)),), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def solve_only():
+        _abi.check(lib.mst_solve_batch(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO,
+                                       coef_d.data_ptr(), dur_d.data_ptr(), info_d.data_ptr(), ws.data_ptr(),
+                                       st), "mst_solve_batch")
+    solve_only()
+    stage_ms["solve"] = timed(solve_only, args.steps) / args.steps
+    nb = min(B, 1 << 16)
+    pos = torch.empty((nb, S_SAMPLES, K_AX), dtype=torch.float64, device=dev)
+    hitb = torch.empty((nb * S_SAMPLES,), dtype=torch.uint8, device=dev)
+
+    def sample_only():
+        _abi.check(lib.mst_sample_batch(coef_d.data_ptr(), dur_d.data_ptr(), nb, N_SEG, K_AX, None, 0, S_SAMPLES,
+                                        0, 0, pos.data_ptr(), None, st), "mst_sample_batch")
+
+    def collide_only():
+        _abi.check(lib.mst_collide_poses(robot.handle, env.handle, pos.data_ptr(), nb * S_SAMPLES, K_AX,
+                                         hitb.data_ptr(), st), "mst_collide_poses")
+    sample_only(); collide_only()
+    stage_ms["sample"] = timed(sample_only, args.steps) / args.steps * (B / nb)
+    stage_ms["collide"] = timed(collide_only, args.steps) / args.steps * (B / nb)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    dominant = max(stage_ms, key=stage_ms.get)
+    # the pipeline's compulsory traffic charged to the whole step: the stages are one logical kernel
+    achieved = B * ALG_BYTES / (ms_per_step * 1e-3) / 1e9 if world == 1 else None
+
+    # --- end to end through HOST buffers (pinned), copies inside the timed region ----------
+    hp = HostPipeline(N_SEG, K_AX, S_SAMPLES, robot, env, chunk=args.e2e_chunk)
+    host_out = HostPipeline.alloc_host_result(B, N_SEG, K_AX, S_SAMPLES)
+
+    def e2e_step():
+        hp.run(wp_host, t_host, host_out)
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    e2e_steps = max(3, args.steps // 4)
+    e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
+    h2d, d2h = hp.bytes_per_trajectory()
+    assert np.array_equal(host_out.any_hit.numpy(), res.any_hit.cpu().numpy())
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4]: %d trajectories/GPU x %d pieces x %d axes, own time vector "
+                               "each (T~U(0.5,2)s), S=%d samples, %s vs %s, seed %d"
+                               % (B, N_SEG, K_AX, S_SAMPLES, ROBOT, ENV, SEED),
+                   "trajectories_per_gpu": B, "l2": "inputs+outputs %.2f GB per step >> 126 MB L2 (no flush needed)"
+                   % (B * (ALG_BYTES + N_SEG * 8 + 4) / 1e9),
+                   "gather": None if world == 1 else "NCCL all_gather of coef(f64)+hit+any_hit in %d chunks, overlapped" % n_chunks,
+                   "solver": "auto (condensed LDL^T; banded pivoted LU for wide duration spreads)"},
+        "clocks": clocks,
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
+                "chunk": hp.chunk, "note": "pinned host in/out, 3-slot copy/compute overlap"},
+        "gpu_launches": args.steps * n_chunks * lib.mst_pipeline_launch_count(cb, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
+                     "peak_source": peak_src, "alg_bytes_per_trajectory": ALG_BYTES,
+                     "kernel": "whole pipeline step (dominant stage: %s)" % dominant,
+                     "stage_ms": stage_ms},
+        "checks": {"solver_failures": bad, "any_hit_rate": hit_rate},
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        nsamp = 256 * cores if not args.quick else 16 * cores
+        arm = CpuArm(cores)
+        arm.run(wp_np[:cores], t_np[:cores])
+        secs = arm.run(wp_np[:nsamp], t_np[:nsamp])
+        arm.close()
+        line["cpu_baseline"] = {"value": nsamp / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "first %d trajectories of the same batch, %.1f s wall on %d processes"
+                                          % (nsamp, secs, cores)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--traj", type=int, default=TRAJ_PER_GPU, help="trajectories per GPU per step")
+    ap.add_argument("--gather-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="tiny CPU sample (smoke runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

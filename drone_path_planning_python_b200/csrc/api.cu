@@ -150,6 +150,15 @@ extern "C" size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_ti
   return solve + align256(chunk * (size_t)S * K * sizeof(double));
 }
 
+extern "C" int mst_pipeline_launch_count(int B, int n, int K, int share_time_group, int solver, int S) {
+  (void)n;
+  if (B <= 0 || S < 1 || K < 1 || share_time_group < 1) return 0;
+  const int chunk = pipeline_chunk(B, K, S, share_time_group);
+  const int chunks = (B + chunk - 1) / chunk;
+  const int solve = solver == MST_SOLVER_AUTO ? 2 : 1;  // condensed (+ banded LU over the declined list)
+  return solve + 2 * chunks + 1;                         // + (sample, collide) per chunk + any_hit
+}
+
 extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
                             int share_time_group, int solver, int S, mst_mesh_t robot, mst_mesh_t env,
                             double* coef, double* dur, int* info, uint8_t* hit, uint8_t* any_hit,

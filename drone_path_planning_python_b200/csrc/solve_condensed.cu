@@ -88,10 +88,10 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
   if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
   const size_t per_thread = sizeof(double) * (size_t)condensed_slots(n, K > 4 ? 4 : K);
   int threads = (int)(MST_MAX_SMEM / per_thread);
-  threads -= threads % 32;
+  if (threads >= 32) threads -= threads % 32;  // long trajectories: a partial warp per CTA still works
   if (threads > 128) threads = 128;
   if (threads > 64 && per_thread * 64 * 3 <= MST_MAX_SMEM) threads = 64;  // more CTAs per SM
-  const bool fits = threads >= 32 && K <= 4;
+  const bool fits = threads >= 8 && K <= 4;
   if (!fits && force) return MST_ERR_TOO_LARGE;
   if (!fits) threads = 32;
   const size_t smem = fits ? per_thread * threads : 0;

@@ -173,6 +173,8 @@ int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double* pose, int 
  *   workspace       mst_pipeline_workspace_bytes(B, n, K, G, S) bytes
  */
 size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_time_group, int S);
+/* number of kernel launches one mst_pipeline call with these sizes issues (for accounting) */
+int mst_pipeline_launch_count(int B, int n, int K, int share_time_group, int solver, int S);
 int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
                  int share_time_group, int solver, int S, mst_mesh_t robot,
                  mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,

@@ -20,8 +20,12 @@ def _soup(name):
     return meshio.triangle_soup(verts, tris)
 
 
-def _random_poses(rng, P, dim):
-    pos = rng.uniform(BOUNDS_LO - 0.5, BOUNDS_HI + 0.5, (P, 3))
+def _random_poses(rng, P, dim, env_tris=None):
+    if env_tris is None:
+        pos = rng.uniform(BOUNDS_LO - 0.5, BOUNDS_HI + 0.5, (P, 3))
+    else:  # around the obstacle, whatever frame the mesh was modelled in
+        flat = env_tris.reshape(-1, 3)
+        pos = rng.uniform(flat.min(axis=0) - 0.8, flat.max(axis=0) + 0.8, (P, 3))
     if dim == 3:
         return pos
     yaw = rng.uniform(-np.pi, np.pi, P)
@@ -41,7 +45,7 @@ def test_collide_poses_vs_oracle(env_name, dim):
     robot_tris, env_tris = _soup("custom_triangle_robot"), _soup(env_name)
     robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
     P = 3000 if len(env_tris) > 24 else 6000
-    poses = _random_poses(rng, P, dim)
+    poses = _random_poses(rng, P, dim, env_tris)
     hit = mst.collide_poses(robot, env, poses).cpu().numpy()
     ref, margin = co.collide_poses(robot_tris, env_tris, poses, with_margin=True)
     clear = np.abs(margin) > EPS
