@@ -1,5 +1,6 @@
 // extern "C" entry points of libmst.so (declared in include/mst.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mst_common.cuh"
@@ -40,10 +41,18 @@ int launch_formation(const double* rb, int F, int m, int pose_dim, const double*
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// trajectories per pass of the unfused pipeline: keeps the sampled positions
-// (chunk*S*K doubles) inside the 126 MB L2 instead of round-tripping through HBM
-static int pipeline_chunk(int B, int K, int S, int G) {
-  long long c = (96ll << 20) / ((long long)S * K * 8);
+int launch_sample_collide(const double* coef, const double* dur, int B, int n, int K, int S,
+                          const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
+                          cudaStream_t stream);
+
+// Trajectories per pass of the pipeline.  The solver writes a chunk's coefficients and the
+// sample+collide kernel reads them back right away, so a chunk is sized to stay resident in
+// the 126 MB L2 (the coefficients then cross HBM once, on their way out).  MST_PIPELINE_CHUNK
+// overrides the size (tuning / experiments).
+static int pipeline_chunk(int B, int n, int K, int G) {
+  long long c = (48ll << 20) / ((long long)n * K * MST_NCOEF * 8);
+  const char* env = getenv("MST_PIPELINE_CHUNK");
+  if (env && atoll(env) > 0) c = atoll(env);
   if (c < G) c = G;
   c -= c % G;
   if (c > B) c = B;
@@ -144,39 +153,39 @@ extern "C" int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double*
 }
 
 extern "C" size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_time_group, int S) {
-  if (B < 0 || S < 0 || K < 1 || share_time_group < 1) return 0;
-  const size_t solve = mst_solve_workspace_bytes(B, n, K, share_time_group);
-  const size_t chunk = (size_t)pipeline_chunk(B > 0 ? B : 1, K, S > 0 ? S : 1, share_time_group);
-  return solve + align256(chunk * (size_t)S * K * sizeof(double));
+  (void)S;
+  if (B < 0 || K < 1 || n < 1 || share_time_group < 1) return 0;
+  return mst_solve_workspace_bytes(B, n, K, share_time_group);
 }
 
 extern "C" int mst_pipeline_launch_count(int B, int n, int K, int share_time_group, int solver, int S) {
-  (void)n;
-  if (B <= 0 || S < 1 || K < 1 || share_time_group < 1) return 0;
-  const int chunk = pipeline_chunk(B, K, S, share_time_group);
+  if (B <= 0 || S < 1 || K < 1 || n < 1 || share_time_group < 1) return 0;
+  const int chunk = pipeline_chunk(B, n, K, share_time_group);
   const int chunks = (B + chunk - 1) / chunk;
   const int solve = solver == MST_SOLVER_AUTO ? 2 : 1;  // condensed (+ banded LU over the declined list)
-  return solve + 2 * chunks + 1;                         // + (sample, collide) per chunk + any_hit
+  return chunks * (solve + 1);                           // + fused sample/collide/any-hit
 }
 
 extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
                             int share_time_group, int solver, int S, mst_mesh_t robot, mst_mesh_t env,
                             double* coef, double* dur, int* info, uint8_t* hit, uint8_t* any_hit,
                             void* workspace, void* stream) {
-  if (S < 1 || (K != 3 && K != 4) || !robot || !env) return MST_ERR_INVALID;
-  if (B > 0 && (!hit || !any_hit || !workspace)) return MST_ERR_INVALID;
-  int rc = mst_solve_batch(wp, t, B, n, K, share_time_group, solver, coef, dur, info, workspace, stream);
-  if (rc != MST_OK || B == 0) return rc;
+  const int G = share_time_group;
+  if (S < 1 || (K != 3 && K != 4) || !robot || !env || G < 1 || B < 0 || n < 1 || B % G != 0)
+    return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!hit || !any_hit || !workspace || !wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  double* pos = (double*)((char*)workspace + mst_solve_workspace_bytes(B, n, K, share_time_group));
-  const int chunk = pipeline_chunk(B, K, S, share_time_group);
+  const int chunk = pipeline_chunk(B, n, K, G);
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
-    rc = launch_sample(coef + (size_t)b0 * n * K * MST_NCOEF, dur + (size_t)b0 * n, nb, n, K, nullptr, 0,
-                       S, MST_SAMPLE_PIECEWISE, 0, pos, nullptr, st);
+    double* cc = coef + (size_t)b0 * n * K * MST_NCOEF;
+    double* dd = dur + (size_t)b0 * n;
+    int rc = mst_solve_batch(wp + (size_t)b0 * (n + 1) * K, t + (size_t)(b0 / G) * (n + 1), nb, n, K, G, solver,
+                             cc, dd, info + b0, workspace, stream);
     if (rc != MST_OK) return rc;
-    rc = launch_collide(robot, env, pos, (long long)nb * S, K, hit + (size_t)b0 * S, st);
+    rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hit + (size_t)b0 * S, any_hit + b0, st);
     if (rc != MST_OK) return rc;
   }
-  return launch_any_hit(hit, B, S, any_hit, st);
+  return MST_OK;
 }

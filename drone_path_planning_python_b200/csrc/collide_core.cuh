@@ -88,4 +88,93 @@ __host__ __device__ inline bool robot_hits_env(const double* R, const double* T,
   return false;
 }
 
+// ---------------------------------------------------------------------------------------
+// Culled mesh-mesh test used by the kernels.  Same answer as robot_hits_env (brute-force
+// SAT over all pairs) away from the touching boundary; every cull is a valid separating
+// axis in exact arithmetic:
+//   1. robot bounding sphere / box against the environment's root box;
+//   2. per environment triangle: robot box against the triangle's box;
+//   3. per environment triangle: the triangle's PLANE against ALL unique robot vertices at
+//      once (the plane is moved into the robot frame: 12 FMAs, then 3 FMAs per vertex) —
+//      this is SAT axis 2 (the env normal) shared by every robot triangle, recorded as
+//      "strictly above" / "strictly below" bit masks over the unique vertices;
+//   4. per robot triangle: skipped when its three corner bits are all above or all below;
+//   5. the 17-axis SAT on the few surviving pairs.
+// ROT = false: translation only (R = identity), the K = 3 pipeline.
+template <bool ROT>
+__host__ __device__ inline bool robot_hits_env_culled(const double* R, const double* T, const MeshView& rb,
+                                                      const MeshBounds& rbb, const MeshView& ev,
+                                                      const MeshBounds& evb, bool rigid) {
+  const double* root = evb.root;
+  if (rigid && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
+                T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
+    return false;
+  // world box of the robot: exact for a translation, else the box of the rotated local box
+  double lo0, lo1, lo2, hi0, hi1, hi2;
+  if (!ROT) {
+    lo0 = rbb.root[0] + T[0]; lo1 = rbb.root[1] + T[1]; lo2 = rbb.root[2] + T[2];
+    hi0 = rbb.root[3] + T[0]; hi1 = rbb.root[4] + T[1]; hi2 = rbb.root[5] + T[2];
+  } else {
+    const double c0 = 0.5 * (rbb.root[0] + rbb.root[3]), c1 = 0.5 * (rbb.root[1] + rbb.root[4]),
+                 c2 = 0.5 * (rbb.root[2] + rbb.root[5]);
+    // half extents, padded so rounding in the products below cannot shrink the box
+    const double h0 = 0.5 * (rbb.root[3] - rbb.root[0]), h1 = 0.5 * (rbb.root[4] - rbb.root[1]),
+                 h2 = 0.5 * (rbb.root[5] - rbb.root[2]);
+    const double pad = 1e-12 * (rbb.radius + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
+    const double w0 = R[0] * c0 + R[1] * c1 + R[2] * c2 + T[0], w1 = R[3] * c0 + R[4] * c1 + R[5] * c2 + T[1],
+                 w2 = R[6] * c0 + R[7] * c1 + R[8] * c2 + T[2];
+    const double e0 = fabs(R[0]) * h0 + fabs(R[1]) * h1 + fabs(R[2]) * h2 + pad,
+                 e1 = fabs(R[3]) * h0 + fabs(R[4]) * h1 + fabs(R[5]) * h2 + pad,
+                 e2 = fabs(R[6]) * h0 + fabs(R[7]) * h1 + fabs(R[8]) * h2 + pad;
+    lo0 = w0 - e0; hi0 = w0 + e0; lo1 = w1 - e1; hi1 = w1 + e1; lo2 = w2 - e2; hi2 = w2 + e2;
+  }
+  if (hi0 < root[0] || lo0 > root[3] || hi1 < root[1] || lo1 > root[4] || hi2 < root[2] || lo2 > root[5])
+    return false;
+  for (int e = 0; e < ev.T; ++e) {
+    const double* bx = ev.box + 6 * e;
+    if (hi0 < bx[0] || lo0 > bx[3] || hi1 < bx[1] || lo1 > bx[4] || hi2 < bx[2] || lo2 > bx[5]) continue;
+    // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
+    const double* pl = ev.plane + 4 * e;
+    double m0, m1, m2;
+    if (ROT) {
+      m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
+      m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
+      m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
+    } else {
+      m0 = pl[0]; m1 = pl[1]; m2 = pl[2];
+    }
+    const double off = pl[0] * T[0] + pl[1] * T[1] + pl[2] * T[2] - pl[3];
+    unsigned long long above = 0ull, below = 0ull;
+    for (int v = 0; v < rb.V; ++v) {
+      const double* p = rb.vert + 3 * v;
+      const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
+      above |= (unsigned long long)(dist > 0.0) << v;
+      below |= (unsigned long long)(dist < 0.0) << v;
+    }
+    const unsigned long long all = rb.V >= 64 ? ~0ull : ((1ull << rb.V) - 1ull);
+    if (above == all || below == all) continue;
+    const double* q = ev.tri + 9 * e;
+    const V3 Q1 = {q[0], q[1], q[2]}, Q2 = {q[3], q[4], q[5]}, Q3 = {q[6], q[7], q[8]};
+    for (int r = 0; r < rb.T; ++r) {
+      const unsigned long long mk = rb.mask[r];
+      if ((above & mk) == mk || (below & mk) == mk) continue;
+      const double* pr = rb.tri + 9 * r;
+      V3 P1, P2, P3;
+      if (ROT) {
+        P1 = xform(R, T, pr); P2 = xform(R, T, pr + 3); P3 = xform(R, T, pr + 6);
+      } else {
+        P1 = {pr[0] + T[0], pr[1] + T[1], pr[2] + T[2]};
+        P2 = {pr[3] + T[0], pr[4] + T[1], pr[5] + T[2]};
+        P3 = {pr[6] + T[0], pr[7] + T[1], pr[8] + T[2]};
+      }
+      if (fmax(fmax(P1.x, P2.x), P3.x) < bx[0] || fmin(fmin(P1.x, P2.x), P3.x) > bx[3] ||
+          fmax(fmax(P1.y, P2.y), P3.y) < bx[1] || fmin(fmin(P1.y, P2.y), P3.y) > bx[4] ||
+          fmax(fmax(P1.z, P2.z), P3.z) < bx[2] || fmin(fmin(P1.z, P2.z), P3.z) > bx[5])
+        continue;
+      if (triangles_intersect(P1, P2, P3, Q1, Q2, Q3)) return true;
+    }
+  }
+  return false;
+}
+
 }  // namespace mst

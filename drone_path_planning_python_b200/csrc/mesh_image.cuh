@@ -1,0 +1,80 @@
+// Host-side construction of the mesh image (layout in mst_common.cuh): unique vertices,
+// corner indices, per-triangle boxes / planes / vertex masks, whole-mesh bounds.
+#pragma once
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mst_common.cuh"
+
+namespace mst {
+
+// returns a malloc'ed image of layout->bytes (>= 16) bytes, or NULL when out of memory
+inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, MeshBounds* bounds) {
+  const size_t nt = (size_t)(T > 0 ? T : 1);
+  int* idx = (int*)malloc(sizeof(int) * 3 * nt);
+  double* uv = (double*)malloc(sizeof(double) * 9 * nt);
+  if (!idx || !uv) { free(idx); free(uv); return NULL; }
+  // unique vertices by exact equality (what the reference's indexed triangles are built on,
+  // src/RigidBodyPlanners/fcl_checker.py:28-40)
+  int V = 0;
+  for (int c = 0; c < 3 * T; ++c) {
+    const double* p = tri + 3 * c;
+    int found = -1;
+    for (int v = 0; v < V && found < 0; ++v)
+      if (uv[3 * v] == p[0] && uv[3 * v + 1] == p[1] && uv[3 * v + 2] == p[2]) found = v;
+    if (found < 0) { found = V; uv[3 * V] = p[0]; uv[3 * V + 1] = p[1]; uv[3 * V + 2] = p[2]; ++V; }
+    idx[c] = found;
+  }
+  *layout = mesh_layout(T, V);
+  char* base = (char*)calloc(1, layout->bytes > 0 ? layout->bytes : 16);
+  if (!base) { free(idx); free(uv); return NULL; }
+  double* itri = (double*)base;
+  double* ibox = (double*)(base + layout->off_box);
+  double* ipl = (double*)(base + layout->off_plane);
+  double* ivert = (double*)(base + layout->off_vert);
+  int* iidx = (int*)(base + layout->off_idx);
+  unsigned long long* imask = (unsigned long long*)(base + layout->off_mask);
+  memcpy(itri, tri, sizeof(double) * 9 * (size_t)T);
+  memcpy(ivert, uv, sizeof(double) * 3 * (size_t)V);
+  memcpy(iidx, idx, sizeof(int) * 3 * (size_t)T);
+  for (int k = 0; k < 3; ++k) { bounds->root[k] = 1e300; bounds->root[3 + k] = -1e300; }
+  bounds->radius = 0.0;
+  for (int t = 0; t < T; ++t) {
+    double* box = ibox + 6 * t;
+    for (int k = 0; k < 3; ++k) { box[k] = 1e300; box[3 + k] = -1e300; }
+    unsigned long long mk = 0ull;
+    for (int c = 0; c < 3; ++c) {
+      double r2 = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        const double v = tri[9 * t + 3 * c + k];
+        if (v < box[k]) box[k] = v;
+        if (v > box[3 + k]) box[3 + k] = v;
+        r2 += v * v;
+      }
+      // rounded up a little: the sphere cull must stay conservative
+      const double r = sqrt(r2) * (1.0 + 1e-12) + 1e-300;
+      if (r > bounds->radius) bounds->radius = r;
+      if (idx[3 * t + c] < 64) mk |= 1ull << idx[3 * t + c];
+    }
+    imask[t] = mk;
+    for (int k = 0; k < 3; ++k) {
+      if (box[k] < bounds->root[k]) bounds->root[k] = box[k];
+      if (box[3 + k] > bounds->root[3 + k]) bounds->root[3 + k] = box[3 + k];
+    }
+    // plane through the triangle: n = (Q2-Q1) x (Q3-Q2), d = n . Q1
+    const double* q = tri + 9 * t;
+    const double f1[3] = {q[3] - q[0], q[4] - q[1], q[5] - q[2]};
+    const double f2[3] = {q[6] - q[3], q[7] - q[4], q[8] - q[5]};
+    double* pl = ipl + 4 * t;
+    pl[0] = f1[1] * f2[2] - f1[2] * f2[1];
+    pl[1] = f1[2] * f2[0] - f1[0] * f2[2];
+    pl[2] = f1[0] * f2[1] - f1[1] * f2[0];
+    pl[3] = pl[0] * q[0] + pl[1] * q[1] + pl[2] * q[2];
+  }
+  free(idx);
+  free(uv);
+  return base;
+}
+
+}  // namespace mst

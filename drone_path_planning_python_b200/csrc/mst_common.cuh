@@ -63,12 +63,67 @@ __device__ __forceinline__ void pose_to_transform(const double* pose, int pose_d
 
 }  // namespace mst
 
-// device-side mesh record behind the opaque mst_mesh_t handle
+// A mesh as the kernels see it: one contiguous, 16-byte-aligned image that a single bulk
+// (TMA) copy stages into shared memory.  Layout in doubles from `base`:
+//   tri[T][9] | box[T][6] | plane[T][4] | vert[V][3] | pad to 16 B | idx[T][3] int32 | pad |
+//   mask[T] uint64 (bit v set when unique vertex v is a corner of the triangle)
+struct MeshView {
+  int T, V;
+  const double* tri;    // corners
+  const double* box;    // per-triangle AABB: min xyz, max xyz
+  const double* plane;  // nx, ny, nz, d  with n = (Q2-Q1) x (Q3-Q2), d = n . Q1
+  const double* vert;   // unique vertices
+  const int* idx;       // corner -> unique vertex
+  const unsigned long long* mask;
+};
+
+struct MeshLayout {
+  int T, V;
+  size_t off_box, off_plane, off_vert, off_idx, off_mask, bytes;  // byte offsets from base
+};
+
+__host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
+  MeshLayout L;
+  L.T = T; L.V = V;
+  size_t o = sizeof(double) * 9 * (size_t)T;
+  L.off_box = o;   o += sizeof(double) * 6 * (size_t)T;
+  L.off_plane = o; o += sizeof(double) * 4 * (size_t)T;
+  L.off_vert = o;  o += sizeof(double) * 3 * (size_t)V;
+  o = (o + 15) & ~(size_t)15;
+  L.off_idx = o;   o += sizeof(int) * 3 * (size_t)T;
+  o = (o + 15) & ~(size_t)15;
+  L.off_mask = o;  o += sizeof(unsigned long long) * (size_t)T;
+  L.bytes = (o + 15) & ~(size_t)15;
+  return L;
+}
+
+__host__ __device__ __forceinline__ MeshView mesh_view(const void* base, const MeshLayout& L) {
+  const char* b = (const char*)base;
+  MeshView v;
+  v.T = L.T; v.V = L.V;
+  v.tri = (const double*)b;
+  v.box = (const double*)(b + L.off_box);
+  v.plane = (const double*)(b + L.off_plane);
+  v.vert = (const double*)(b + L.off_vert);
+  v.idx = (const int*)(b + L.off_idx);
+  v.mask = (const unsigned long long*)(b + L.off_mask);
+  return v;
+}
+
+// whole-mesh bounds, passed to kernels by value
+struct MeshBounds {
+  double root[6];   // AABB in the mesh's own frame
+  double radius;    // max |vertex|, rounded up: bound of the mesh under any rotation about its origin
+};
+
+// host-side record behind the opaque mst_mesh_t handle
 struct mst_mesh {
-  int T;             // triangle count
-  double* d_tri;     // [T][9]   corners, device
-  double* d_box;     // [T][6]   per-triangle AABB (min xyz, max xyz), device
-  double root[6];    // AABB of the whole mesh (host copy)
-  double radius;     // max |vertex| (bound of the mesh under any rotation about its origin)
-  double* h_tri;     // host copy of the corners (for packing into constant/shared memory)
+  int T, V;
+  MeshLayout layout;
+  void* d_image;       // device copy of the image
+  void* h_image;       // host copy
+  MeshBounds bounds;
+  // views into the device image kept for the kernels that take raw arrays
+  double* d_tri;
+  double* d_box;
 };

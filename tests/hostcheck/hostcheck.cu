@@ -7,6 +7,7 @@
 
 #include "../../drone_path_planning_python_b200/csrc/collide_core.cuh"
 #include "../../drone_path_planning_python_b200/csrc/condensed_core.cuh"
+#include "../../drone_path_planning_python_b200/csrc/mesh_image.cuh"
 
 using namespace mst;
 
@@ -49,4 +50,25 @@ extern "C" int hostcheck_collide(const double* robot_tri, int Tr, const double* 
     hit[p] = robot_hits_env(R + 9 * (size_t)p, T + 3 * (size_t)p, robot_tri, Tr, env_tri, env_box, Te, root,
                             radius, rigid != 0) ? 1 : 0;
   return 0;
+}
+
+// the culled mesh-mesh routine the kernels use, on meshes given as triangle soups
+extern "C" int hostcheck_collide_culled(const double* robot_tri, int Tr, const double* env_tri, int Te,
+                                        const double* R, const double* T, int P, int rot, int rigid,
+                                        unsigned char* hit) {
+  MeshLayout rl, el;
+  MeshBounds rbb, evb;
+  void* ri = build_mesh_image(robot_tri, Tr, &rl, &rbb);
+  void* ei = build_mesh_image(env_tri, Te, &el, &evb);
+  if (!ri || !ei) return -1;
+  const MeshView rb = mesh_view(ri, rl), ev = mesh_view(ei, el);
+  for (int p = 0; p < P; ++p) {
+    const double* Rp = R + 9 * (size_t)p;
+    const double* Tp = T + 3 * (size_t)p;
+    hit[p] = (rot ? robot_hits_env_culled<true>(Rp, Tp, rb, rbb, ev, evb, rigid != 0)
+                  : robot_hits_env_culled<false>(Rp, Tp, rb, rbb, ev, evb, rigid != 0)) ? 1 : 0;
+  }
+  free(ri);
+  free(ei);
+  return rb.V;
 }
