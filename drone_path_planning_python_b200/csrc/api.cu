@@ -45,12 +45,14 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
                           const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
                           cudaStream_t stream);
 
-// Trajectories per pass of the pipeline.  The solver writes a chunk's coefficients and the
-// sample+collide kernel reads them back right away, so a chunk is sized to stay resident in
-// the 126 MB L2 (the coefficients then cross HBM once, on their way out).  MST_PIPELINE_CHUNK
-// overrides the size (tuning / experiments).
+// Trajectories per pass of the pipeline (solver launch + fused sample/collide launch).
+// Measured on B200 (profiles/r1_chunk_sweep.txt): passes small enough to keep a pass's
+// coefficients L2-resident between the two kernels (~26 k trajectories) lose more to launch
+// gaps and tail effects than the saved re-read is worth (18.6 ms vs 11.7 ms per 1 M), so a
+// pass is as large as 32-bit indexing comfortably allows.  MST_PIPELINE_CHUNK overrides it.
 static int pipeline_chunk(int B, int n, int K, int G) {
-  long long c = (48ll << 20) / ((long long)n * K * MST_NCOEF * 8);
+  long long c = 1ll << 22;
+  (void)n; (void)K;
   const char* env = getenv("MST_PIPELINE_CHUNK");
   if (env && atoll(env) > 0) c = atoll(env);
   if (c < G) c = G;

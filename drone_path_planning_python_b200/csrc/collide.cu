@@ -29,26 +29,47 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
                const double* __restrict__ pose, long long P, int pose_dim, uint8_t* __restrict__ hit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
+  __shared__ unsigned work_queue[4][65];  // per warp: 64-entry ring + hit mask
+  unsigned* wq = work_queue[threadIdx.x >> 5];
   stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
   const MeshView rb = mesh_view(smem_raw, rl);
   const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
-  const bool culled = rb.V <= 64;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < P;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const double* ps = pose + idx * pose_dim;
-    double R[9], T[3];
+  const bool culled = rb.V <= 64 && rb.T < 4096 && ev.T < 4096;
+  // warp-uniform trip count (the collision test votes across the warp)
+  for (long long base = blockIdx.x * (long long)blockDim.x; base < P; base += (long long)gridDim.x * blockDim.x) {
+    const long long idx = base + threadIdx.x;
+    const bool active = idx < P;
+    const double* ps = pose + (active ? idx : P - 1) * pose_dim;
     bool h;
     if (pose_dim == 3) {
-      T[0] = ps[0]; T[1] = ps[1]; T[2] = ps[2];
-      R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-      h = culled ? robot_hits_env_culled<false>(R, T, rb, rbb, ev, evb, true)
-                 : robot_hits_env(R, T, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+      const double pp[3] = {ps[0], ps[1], ps[2]};
+      if (culled) {
+        h = robot_hits_env_queue<0>(active, pp, rb, rbb, ev, evb, wq);
+      } else {
+        const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+      }
+    } else if (pose_dim == 4) {
+      double pp[5] = {ps[0], ps[1], ps[2], 0.0, 0.0};
+      sincos(ps[3] * 0.5, &pp[3], &pp[4]);
+      if (culled) {
+        h = robot_hits_env_queue<1>(active, pp, rb, rbb, ev, evb, wq);
+      } else {
+        double R[9];
+        quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
+        h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+      }
     } else {
-      pose_to_transform(ps, pose_dim, R, T);
-      h = culled ? robot_hits_env_culled<true>(R, T, rb, rbb, ev, evb, pose_dim != 7)
-                 : robot_hits_env(R, T, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, pose_dim != 7);
+      const double pp[7] = {ps[0], ps[1], ps[2], ps[3], ps[4], ps[5], ps[6]};
+      if (culled) {
+        h = robot_hits_env_queue<2>(active, pp, rb, rbb, ev, evb, wq);
+      } else {
+        double R[9];
+        quat_to_matrix(pp[3], pp[4], pp[5], pp[6], R);
+        h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, false);
+      }
     }
-    hit[idx] = h ? 1 : 0;
+    if (active) hit[idx] = h ? 1 : 0;
   }
 }
 

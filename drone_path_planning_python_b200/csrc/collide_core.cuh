@@ -52,6 +52,68 @@ __host__ __device__ inline bool triangles_intersect(V3 P1, V3 P2, V3 P3, V3 Q1, 
   return true;
 }
 
+// Interval form of the triangle-triangle test (Moller, "A fast triangle-triangle intersection
+// test", 1997, division-free variant): both triangles must straddle (or touch) the other's
+// plane; they then meet the line where the two planes cross in one interval each, and
+// intersect iff the two intervals overlap.  In exact arithmetic this is the same predicate
+// as the 17-axis SAT for non-coplanar triangles — closed triangles, touching counts — at a
+// fraction of the operations (the nine edge-edge axes collapse into one interval
+// comparison).  Parallel / coplanar / degenerate pairs (plane normals not independent) go
+// to the 17-axis test, which is what decides them in FCL too.  The two predicates can only
+// disagree inside the rounding band around touching configurations.
+__host__ __device__ __forceinline__ bool interval_terms(double v0, double v1, double v2, double d0, double d1,
+                                                        double d2, double& a, double& b, double& c, double& x0,
+                                                        double& x1) {
+  if (d0 * d1 > 0.0) {            // v2 alone on its side (or on the plane)
+    a = v2; b = (v0 - v2) * d2; c = (v1 - v2) * d2; x0 = d2 - d0; x1 = d2 - d1;
+  } else if (d0 * d2 > 0.0) {     // v1 alone
+    a = v1; b = (v0 - v1) * d1; c = (v2 - v1) * d1; x0 = d1 - d0; x1 = d1 - d2;
+  } else if (d1 * d2 > 0.0 || d0 != 0.0) {  // v0 alone
+    a = v0; b = (v1 - v0) * d0; c = (v2 - v0) * d0; x0 = d0 - d1; x1 = d0 - d2;
+  } else if (d1 != 0.0) {
+    a = v1; b = (v0 - v1) * d1; c = (v2 - v1) * d1; x0 = d1 - d0; x1 = d1 - d2;
+  } else if (d2 != 0.0) {
+    a = v2; b = (v0 - v2) * d2; c = (v1 - v2) * d2; x0 = d2 - d0; x1 = d2 - d1;
+  } else {
+    return false;                 // the triangle lies in the other plane
+  }
+  return true;
+}
+
+__host__ __device__ inline bool triangles_intersect_interval(V3 P1, V3 P2, V3 P3, V3 Q1, V3 Q2, V3 Q3) {
+  // same translation as the SAT: everything relative to P1
+  const V3 p2 = sub(P2, P1), p3 = sub(P3, P1);
+  const V3 q1 = sub(Q1, P1), q2 = sub(Q2, P1), q3 = sub(Q3, P1);
+  const V3 n2 = cross(sub(q2, q1), sub(q3, q2));
+  const double c2 = dot(n2, q1);
+  const double dp1 = -c2, dp2 = dot(n2, p2) - c2, dp3 = dot(n2, p3) - c2;
+  if ((dp1 > 0.0 && dp2 > 0.0 && dp3 > 0.0) || (dp1 < 0.0 && dp2 < 0.0 && dp3 < 0.0)) return false;
+  const V3 n1 = cross(p2, sub(p3, p2));
+  const double dq1 = dot(n1, q1), dq2 = dot(n1, q2), dq3 = dot(n1, q3);
+  if ((dq1 > 0.0 && dq2 > 0.0 && dq3 > 0.0) || (dq1 < 0.0 && dq2 < 0.0 && dq3 < 0.0)) return false;
+  const V3 D = cross(n1, n2);
+  const double ax = fabs(D.x), ay = fabs(D.y), az = fabs(D.z);
+  const double dmax = fmax(ax, fmax(ay, az));
+  // normals (numerically) dependent: parallel planes, coplanar or degenerate triangles
+  const double scale = (fabs(n1.x) + fabs(n1.y) + fabs(n1.z)) * (fabs(n2.x) + fabs(n2.y) + fabs(n2.z));
+  if (!(dmax > 1e-12 * scale)) return triangles_intersect(P1, P2, P3, Q1, Q2, Q3);
+  double pv1, pv2, pv3, qv1, qv2, qv3;  // coordinate along the dominant axis of the line
+  if (ax >= ay && ax >= az) { pv1 = 0.0; pv2 = p2.x; pv3 = p3.x; qv1 = q1.x; qv2 = q2.x; qv3 = q3.x; }
+  else if (ay >= az)        { pv1 = 0.0; pv2 = p2.y; pv3 = p3.y; qv1 = q1.y; qv2 = q2.y; qv3 = q3.y; }
+  else                      { pv1 = 0.0; pv2 = p2.z; pv3 = p3.z; qv1 = q1.z; qv2 = q2.z; qv3 = q3.z; }
+  double a, b, c, x0, x1, d, e, f, y0, y1;
+  if (!interval_terms(pv1, pv2, pv3, dp1, dp2, dp3, a, b, c, x0, x1) ||
+      !interval_terms(qv1, qv2, qv3, dq1, dq2, dq3, d, e, f, y0, y1))
+    return triangles_intersect(P1, P2, P3, Q1, Q2, Q3);
+  const double xx = x0 * x1, yy = y0 * y1, xxyy = xx * yy;
+  double t = a * xxyy;
+  const double i10 = t + b * x1 * yy, i11 = t + c * x0 * yy;
+  t = d * xxyy;
+  const double i20 = t + e * xx * y1, i21 = t + f * xx * y0;
+  const double lo1 = fmin(i10, i11), hi1 = fmax(i10, i11), lo2 = fmin(i20, i21), hi2 = fmax(i20, i21);
+  return !(hi1 < lo2 || hi2 < lo1);
+}
+
 __host__ __device__ __forceinline__ V3 xform(const double* R, const double* T, const double* v) {
   return {R[0] * v[0] + R[1] * v[1] + R[2] * v[2] + T[0],
           R[3] * v[0] + R[4] * v[1] + R[5] * v[2] + T[1],
@@ -176,5 +238,156 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
   }
   return false;
 }
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative form of robot_hits_env_culled with WORK COMPACTION: lane <-> pose for the
+// broad phase, lane <-> (pose, robot triangle, env triangle) item for the narrow phase.
+//
+// A profile of the per-lane version (profiles/r1a_*) showed ~86 % of all issued
+// instructions inside the SAT with 4.5 of 32 lanes active: neighbouring poses survive the
+// culls with DIFFERENT triangle pairs, so the lanes serialise.  Here the broad phase
+// (bounding boxes, the env plane against all robot vertices, the vertex masks — the very
+// same predicates) only ENQUEUES surviving (lane, e, r) triples into a 64-entry ring in
+// shared memory, using warp ballots for the slots; whenever 32 items are waiting the warp
+// runs the SAT on 32 different items at once (the pose of the item's source lane comes by
+// shuffle), and a hit is OR-ed into a per-warp bit mask.  The pair test is the interval
+// form (triangles_intersect_interval), equal to the 17-axis SAT away from touching.
+//
+// POSE: 0 translation (x,y,z); 1 yaw (x,y,z,sin(yaw/2),cos(yaw/2)); 2 quaternion
+// (x,y,z,qx,qy,qz,qw).  wq: 65 unsigned of shared memory owned by this warp.
+template <int POSE> struct PoseDim { static constexpr int N = POSE == 0 ? 3 : (POSE == 1 ? 5 : 7); };
+
+template <int POSE>
+__device__ __forceinline__ void pose_rotation(const double* pp, double* R) {
+  if (POSE == 1) quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
+  if (POSE == 2) quat_to_matrix(pp[3], pp[4], pp[5], pp[6], R);
+}
+
+template <int POSE>
+__device__ __forceinline__ void narrow_phase_items(int count, unsigned head, const double* pp, const MeshView& rb,
+                                                   const MeshView& ev, unsigned* wq) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool valid = lane < count;
+  const unsigned item = valid ? wq[(head + lane) & 63u] : 0u;
+  const int src = valid ? (int)(item >> 24) : lane;
+  const int e = (int)((item >> 12) & 0xfffu), r = (int)(item & 0xfffu);
+  double q[PoseDim<POSE>::N];
+#pragma unroll
+  for (int i = 0; i < PoseDim<POSE>::N; ++i) q[i] = __shfl_sync(FULL, pp[i], src);
+  if (valid && !((wq[64] >> src) & 1u)) {
+    const double* pr = rb.tri + 9 * r;
+    V3 P1, P2, P3;
+    if (POSE == 0) {
+      P1 = {pr[0] + q[0], pr[1] + q[1], pr[2] + q[2]};
+      P2 = {pr[3] + q[0], pr[4] + q[1], pr[5] + q[2]};
+      P3 = {pr[6] + q[0], pr[7] + q[1], pr[8] + q[2]};
+    } else {
+      double R[9];
+      pose_rotation<POSE>(q, R);
+      P1 = xform(R, q, pr); P2 = xform(R, q, pr + 3); P3 = xform(R, q, pr + 6);
+    }
+    const double* bx = ev.box + 6 * e;
+    if (!(fmax(fmax(P1.x, P2.x), P3.x) < bx[0] || fmin(fmin(P1.x, P2.x), P3.x) > bx[3] ||
+          fmax(fmax(P1.y, P2.y), P3.y) < bx[1] || fmin(fmin(P1.y, P2.y), P3.y) > bx[4] ||
+          fmax(fmax(P1.z, P2.z), P3.z) < bx[2] || fmin(fmin(P1.z, P2.z), P3.z) > bx[5])) {
+      const double* qe = ev.tri + 9 * e;
+      const V3 Q1 = {qe[0], qe[1], qe[2]}, Q2 = {qe[3], qe[4], qe[5]}, Q3 = {qe[6], qe[7], qe[8]};
+      if (triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3)) atomicOr(&wq[64], 1u << src);
+    }
+  }
+  __syncwarp();
+}
+
+template <int POSE>
+__device__ __forceinline__ bool robot_hits_env_queue(bool active, const double* pp, const MeshView& rb,
+                                                     const MeshBounds& rbb, const MeshView& ev,
+                                                     const MeshBounds& evb, unsigned* wq) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const double* root = evb.root;
+  const double* T = pp;
+  bool near = active;
+  // POSE 2 takes whatever quaternion the caller gave (maybe not unit): no sphere cull there
+  if (POSE != 2 && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
+                    T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
+    near = false;
+  if (!__any_sync(FULL, near)) return false;
+  double R[9];
+  pose_rotation<POSE>(pp, R);
+  double lo0, lo1, lo2, hi0, hi1, hi2;
+  if (POSE == 0) {
+    lo0 = rbb.root[0] + T[0]; lo1 = rbb.root[1] + T[1]; lo2 = rbb.root[2] + T[2];
+    hi0 = rbb.root[3] + T[0]; hi1 = rbb.root[4] + T[1]; hi2 = rbb.root[5] + T[2];
+  } else {
+    const double c0 = 0.5 * (rbb.root[0] + rbb.root[3]), c1 = 0.5 * (rbb.root[1] + rbb.root[4]),
+                 c2 = 0.5 * (rbb.root[2] + rbb.root[5]);
+    const double h0 = 0.5 * (rbb.root[3] - rbb.root[0]), h1 = 0.5 * (rbb.root[4] - rbb.root[1]),
+                 h2 = 0.5 * (rbb.root[5] - rbb.root[2]);
+    const double pad = 1e-12 * (rbb.radius + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
+    const double w0 = R[0] * c0 + R[1] * c1 + R[2] * c2 + T[0], w1 = R[3] * c0 + R[4] * c1 + R[5] * c2 + T[1],
+                 w2 = R[6] * c0 + R[7] * c1 + R[8] * c2 + T[2];
+    const double e0 = fabs(R[0]) * h0 + fabs(R[1]) * h1 + fabs(R[2]) * h2 + pad,
+                 e1 = fabs(R[3]) * h0 + fabs(R[4]) * h1 + fabs(R[5]) * h2 + pad,
+                 e2 = fabs(R[6]) * h0 + fabs(R[7]) * h1 + fabs(R[8]) * h2 + pad;
+    lo0 = w0 - e0; hi0 = w0 + e0; lo1 = w1 - e1; hi1 = w1 + e1; lo2 = w2 - e2; hi2 = w2 + e2;
+  }
+  if (hi0 < root[0] || lo0 > root[3] || hi1 < root[1] || lo1 > root[4] || hi2 < root[2] || lo2 > root[5])
+    near = false;
+  if (!__any_sync(FULL, near)) return false;
+  if (lane == 0) wq[64] = 0u;
+  __syncwarp();
+  unsigned head = 0u, tail = 0u;  // ring positions (warp-uniform)
+  const unsigned long long all = rb.V >= 64 ? ~0ull : ((1ull << rb.V) - 1ull);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int e = 0; e < ev.T; ++e) {
+    const double* bx = ev.box + 6 * e;
+    bool pass = near && !(hi0 < bx[0] || lo0 > bx[3] || hi1 < bx[1] || lo1 > bx[4] || hi2 < bx[2] || lo2 > bx[5]);
+    if (!__any_sync(FULL, pass)) continue;
+    unsigned long long above = 0ull, below = 0ull;
+    if (pass) {
+      const double* pl = ev.plane + 4 * e;
+      double m0, m1, m2;
+      if (POSE != 0) {
+        m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
+        m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
+        m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
+      } else {
+        m0 = pl[0]; m1 = pl[1]; m2 = pl[2];
+      }
+      const double off = pl[0] * T[0] + pl[1] * T[1] + pl[2] * T[2] - pl[3];
+      for (int v = 0; v < rb.V; ++v) {
+        const double* p = rb.vert + 3 * v;
+        const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
+        above |= (unsigned long long)(dist > 0.0) << v;
+        below |= (unsigned long long)(dist < 0.0) << v;
+      }
+      if (above == all || below == all) pass = false;
+    }
+    if (!__any_sync(FULL, pass)) continue;
+    for (int r = 0; r < rb.T; ++r) {
+      const unsigned long long mk = rb.mask[r];
+      const bool need = pass && !((above & mk) == mk || (below & mk) == mk);
+      const unsigned vote = __ballot_sync(FULL, need);
+      if (!vote) continue;
+      if (need) wq[(tail + __popc(vote & lt_mask)) & 63u] = ((unsigned)lane << 24) | ((unsigned)e << 12) | (unsigned)r;
+      tail += __popc(vote);
+      if (tail - head >= 32u) {
+        __syncwarp();
+        narrow_phase_items<POSE>(32, head, pp, rb, ev, wq);
+        head += 32u;
+        // poses already known to collide stop producing work
+        if ((wq[64] >> lane) & 1u) near = false;
+        pass = pass && near;
+      }
+    }
+    if (!__any_sync(FULL, near)) break;
+  }
+  __syncwarp();
+  if (tail != head) narrow_phase_items<POSE>((int)(tail - head), head, pp, rb, ev, wq);
+  return active && ((wq[64] >> lane) & 1u);
+}
+#endif  // __CUDACC__
 
 }  // namespace mst

@@ -12,10 +12,10 @@
 // positions never leave registers; only hit[B][S] (1 byte per sample, coalesced) and
 // any_hit[B] are written.
 //
-// Mapping: a CTA walks tiles of TB trajectories; inside a tile the (trajectory, sample)
-// pairs are flattened over the threads, so a warp holds 32 CONSECUTIVE samples of one
-// trajectory (neighbouring poses: the culling decisions of the lanes agree and the
-// coefficient loads are warp-wide broadcasts).
+// Mapping: a WARP walks tiles of 4 trajectories; inside a tile the (trajectory, sample)
+// pairs are flattened over the lanes, so a warp holds 32 CONSECUTIVE samples of one
+// trajectory (neighbouring poses: coefficient loads are warp-wide broadcasts, the broad
+// phase decisions mostly agree) and the narrow phase is compacted across the warp.
 //
 // The evaluation is bit-identical to mst_sample_batch (same running-sum piece search, same
 // non-fused Horner), so pipeline flags equal "sample, then collide" exactly.
@@ -24,45 +24,58 @@
 
 namespace mst {
 
-constexpr int FUSED_THREADS = 256;
-constexpr int FUSED_TB = 32;  // trajectories per tile
+constexpr int FUSED_THREADS = 128;
+constexpr int FUSED_WARPS = FUSED_THREADS / 32;
+constexpr int FUSED_WT = 4;  // trajectories per warp tile
 
+// Every WARP walks its own tiles of FUSED_WT trajectories (no CTA-wide barrier after the
+// meshes are staged): a warp that meets the obstacle takes several times longer over a
+// tile than one that flies in free space, and a CTA barrier per tile made the fast warps
+// wait (27 % of all warp-stall samples in profiles/r1b).
 template <int K>
-__global__ void __launch_bounds__(FUSED_THREADS)
+__global__ void __launch_bounds__(FUSED_THREADS, 4)
 sample_collide_kernel(const double* __restrict__ coef, const double* __restrict__ dur, int B, int n, int S,
                       const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
                       const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
                       uint8_t* __restrict__ hit, uint8_t* __restrict__ any_hit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ int any_flag[FUSED_TB];
+  __shared__ int any_flag[FUSED_WARPS][FUSED_WT];
+  __shared__ unsigned work_queue[FUSED_WARPS][65];  // per warp: 64-entry ring + hit mask
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned* wq = work_queue[warp];
   stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
   const MeshView rb = mesh_view(smem_raw, rl);
   const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
-  const bool culled = rb.V <= 64;
-  // per-tile tables behind the meshes: knots[TB][n+1] (running sums), dt[TB]
-  double* knots = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
-  double* dts = knots + FUSED_TB * (n + 1);
+  const bool culled = rb.V <= 64 && rb.T < 4096 && ev.T < 4096;
+  // per-warp tables behind the meshes: knots[WT][n+1] (running sums), dt[WT]
+  double* knots = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes) + warp * FUSED_WT * (n + 2);
+  double* dts = knots + FUSED_WT * (n + 1);
 
-  const int tiles = (B + FUSED_TB - 1) / FUSED_TB;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int b0 = tile * FUSED_TB;
-    const int nb = min(FUSED_TB, B - b0);
-    __syncthreads();  // previous tile's tables are no longer read
-    if (threadIdx.x < nb) {
-      const double* T = dur + (size_t)(b0 + threadIdx.x) * n;
-      double* kn = knots + threadIdx.x * (n + 1);
+  const int tiles = (B + FUSED_WT - 1) / FUSED_WT;
+  for (int tile = blockIdx.x * FUSED_WARPS + warp; tile < tiles; tile += gridDim.x * FUSED_WARPS) {
+    const int b0 = tile * FUSED_WT;
+    const int nb = min(FUSED_WT, B - b0);
+    __syncwarp();  // previous tile's tables are no longer read
+    if (lane < nb) {
+      const double* T = dur + (size_t)(b0 + lane) * n;
+      double* kn = knots + lane * (n + 1);
       double acc = 0.0;
       kn[0] = 0.0;
       for (int i = 0; i < n; ++i) { acc = __dadd_rn(acc, T[i]); kn[i + 1] = acc; }
-      dts[threadIdx.x] = __ddiv_rn(acc, (double)S);
-      any_flag[threadIdx.x] = 0;
+      dts[lane] = __ddiv_rn(acc, (double)S);
+      any_flag[warp][lane] = 0;
     }
-    __syncthreads();
+    __syncwarp();
     const int work = nb * S;
-    for (int idx = threadIdx.x; idx < work; idx += FUSED_THREADS) {
-      const int tl = idx / S;
-      const int s = idx - tl * S;
+    // warp-uniform trip count: every lane stays in the loop (the collision test votes
+    // across the warp), lanes past the end of the tile are simply inactive
+    for (int base = 0; base < work; base += 32) {
+      const int idx = base + lane;
+      const bool active = idx < work;
+      const int cidx = active ? idx : work - 1;
+      const int tl = cidx / S;
+      const int s = cidx - tl * S;
       const double* kn = knots + tl * (n + 1);
       const double t = __dmul_rn((double)s, dts[tl]);
       // PiecewisePolynomial.eval: first piece with t < acc + T_i, else the last one at
@@ -87,24 +100,32 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
         x = __dadd_rn(__dmul_rn(x, local), c01.x);
         pos[k] = x;
       }
-      double R[9], T[3] = {pos[0], pos[1], pos[2]};
       bool h;
       if (K == 3) {
-        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-        h = culled ? robot_hits_env_culled<false>(R, T, rb, rbb, ev, evb, true)
-                   : robot_hits_env(R, T, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+        if (culled) {
+          h = robot_hits_env_queue<0>(active, pos, rb, rbb, ev, evb, wq);
+        } else {
+          const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+          h = active && robot_hits_env(R, pos, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+        }
       } else {
-        double sn, cs;
-        sincos(pos[K - 1] * 0.5, &sn, &cs);
-        quat_to_matrix(0.0, 0.0, sn, cs, R);
-        h = culled ? robot_hits_env_culled<true>(R, T, rb, rbb, ev, evb, true)
-                   : robot_hits_env(R, T, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+        double pp[5] = {pos[0], pos[1], pos[2], 0.0, 0.0};
+        sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
+        if (culled) {
+          h = robot_hits_env_queue<1>(active, pp, rb, rbb, ev, evb, wq);
+        } else {
+          double R[9];
+          quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
+          h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+        }
       }
-      hit[(size_t)b0 * S + idx] = h ? 1 : 0;
-      if (h) any_flag[tl] = 1;  // benign race: every writer stores 1
+      if (active) {
+        hit[(size_t)b0 * S + idx] = h ? 1 : 0;
+        if (h) any_flag[warp][tl] = 1;  // benign race: every writer stores 1
+      }
     }
-    __syncthreads();
-    if (threadIdx.x < nb) any_hit[b0 + threadIdx.x] = any_flag[threadIdx.x] ? 1 : 0;
+    __syncwarp();
+    if (lane < nb) any_hit[b0 + lane] = any_flag[warp][lane] ? 1 : 0;
   }
 }
 
@@ -112,16 +133,16 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
                           const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
                           cudaStream_t stream) {
   if (B == 0) return MST_OK;
-  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * FUSED_TB * (size_t)(n + 2);
+  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * FUSED_WARPS * FUSED_WT * (size_t)(n + 2);
   if (smem > MST_MAX_SMEM - 2048) return MST_ERR_TOO_LARGE;
   auto kern = K == 3 ? sample_collide_kernel<3> : sample_collide_kernel<4>;
   if (smem > 40 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MST_MAX_SMEM);
     if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
   }
-  const int tiles = (B + FUSED_TB - 1) / FUSED_TB;
-  int blocks = tiles;
-  const int cap = MST_SM_COUNT * 8;  // persistent CTAs; tiles are walked in a grid-stride loop
+  const int tiles = (B + FUSED_WT - 1) / FUSED_WT;
+  int blocks = (tiles + FUSED_WARPS - 1) / FUSED_WARPS;
+  const int cap = MST_SM_COUNT * 4;  // persistent CTAs (4 resident per SM); warps stride over the tiles
   if (blocks > cap) blocks = cap;
   kern<<<blocks, FUSED_THREADS, smem, stream>>>(coef, dur, B, n, S, robot->d_image, robot->layout,
                                                  robot->bounds, env->d_image, env->layout, env->bounds, hit,

@@ -72,3 +72,15 @@ extern "C" int hostcheck_collide_culled(const double* robot_tri, int Tr, const d
   free(ei);
   return rb.V;
 }
+
+// pairwise triangle tests: tri[N][2][3][3]; out17 = 17-axis SAT, outi = interval form
+extern "C" int hostcheck_tri_pairs(const double* tri, int N, unsigned char* out17, unsigned char* outi) {
+  for (int i = 0; i < N; ++i) {
+    const double* t = tri + 18 * (size_t)i;
+    const V3 P1 = {t[0], t[1], t[2]}, P2 = {t[3], t[4], t[5]}, P3 = {t[6], t[7], t[8]};
+    const V3 Q1 = {t[9], t[10], t[11]}, Q2 = {t[12], t[13], t[14]}, Q3 = {t[15], t[16], t[17]};
+    out17[i] = triangles_intersect(P1, P2, P3, Q1, Q2, Q3) ? 1 : 0;
+    outi[i] = triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3) ? 1 : 0;
+  }
+  return 0;
+}
