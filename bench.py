@@ -226,29 +226,23 @@ def run_ours(args):
                              torch.empty((B,), dtype=torch.uint8, device=dev))
 
     # multi-GPU: chunked all-gather of coefficients + flags, overlapped with the next chunk
-    n_chunks = args.gather_chunks if world > 1 else 1
-    cb = B // n_chunks
-    gathered = None
+    from drone_path_planning_python_b200.distributed import ChunkedAllGather
+    gather = None
+    n_chunks = 1
     if world > 1:
-        gathered = [(torch.empty((world, cb, N_SEG, K_AX, 8), dtype=torch.float64, device=dev),
-                     torch.empty((world, cb, S_SAMPLES), dtype=torch.uint8, device=dev),
-                     torch.empty((world, cb), dtype=torch.uint8, device=dev)) for _ in range(n_chunks)]
+        gather = ChunkedAllGather(B, world, args.gather_chunks, [res.coef, res.hit, res.any_hit])
+        n_chunks = len(gather.plan)
+
+    def compute_chunk(lo, hi):
+        view = mst.PipelineResult(res.coef[lo:hi], res.dur[lo:hi], res.info[lo:hi], res.hit[lo:hi], res.any_hit[lo:hi])
+        mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
+        return view.coef, view.hit, view.any_hit
 
     def step():
         if world == 1:
             mst.pipeline(wp, t, S_SAMPLES, robot, env, out=res)
-            return
-        handles = []
-        for c in range(n_chunks):
-            sl = slice(c * cb, (c + 1) * cb)
-            view = mst.PipelineResult(res.coef[sl], res.dur[sl], res.info[sl], res.hit[sl], res.any_hit[sl])
-            mst.pipeline(wp[sl], t[sl], S_SAMPLES, robot, env, out=view)
-            g = gathered[c]
-            handles.append(dist.all_gather_into_tensor(g[0], view.coef, async_op=True))
-            handles.append(dist.all_gather_into_tensor(g[1], view.hit, async_op=True))
-            handles.append(dist.all_gather_into_tensor(g[2], view.any_hit, async_op=True))
-        for h in handles:
-            h.wait()
+        else:
+            gather.run(compute_chunk, assemble=False)   # results stay in [chunk][rank][...] staging buffers
 
     def barrier():
         if world > 1:
@@ -346,7 +340,7 @@ def run_ours(args):
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
                 "chunk": hp.chunk, "note": "pinned host in/out, 3-slot copy/compute overlap"},
-        "gpu_launches": args.steps * n_chunks * lib.mst_pipeline_launch_count(cb, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES),
+        "gpu_launches": args.steps * n_chunks * lib.mst_pipeline_launch_count(B // n_chunks, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
                      "peak_source": peak_src, "alg_bytes_per_trajectory": ALG_BYTES,

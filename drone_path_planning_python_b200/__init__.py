@@ -9,7 +9,8 @@ device every call raises.
 """
 from . import _abi  # noqa: F401
 from .batch import (Mesh, PipelineResult, collide_poses, flat_outputs, formation_waypoints,  # noqa: F401
-                    pipeline, sample_batch, solve_batch, time_power_rows)
+                    pack_pol_matrix, pipeline, poly_derivative, poly_terms_at_t, sample_batch, solve_batch,
+                    time_power_rows)
 
 __version__ = "0.1.0"
 

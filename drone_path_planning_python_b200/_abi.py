@@ -23,10 +23,14 @@ PROTOTYPES = {
     "mst_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "mst_last_cuda_error": (ctypes.c_char_p, []),
     "mst_time_power_rows": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p]),
+    "mst_poly_derivative": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p]),
+    "mst_poly_terms_at_t": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p]),
     "mst_solve_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
     "mst_solve_batch": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p]),
+    "mst_pack_pol_matrix": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           c_void_p, c_void_p]),
     "mst_sample_batch": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_void_p, c_void_p, c_void_p]),

@@ -49,6 +49,35 @@ def time_power_rows(t) -> torch.Tensor:
     return rows
 
 
+def poly_derivative(p) -> torch.Tensor:
+    """``p[count, len]`` -> ``[count, len-1]``: ``(i+1) * p[i+1]``
+    (reference: Polynomial.derivative, src/optimizations/uav_trajectory.py:25-26)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    pp = _f64(p, dev)
+    if pp.dim() == 1:
+        pp = pp[None]
+    count, ln = pp.shape
+    out = torch.empty((count, max(ln - 1, 0)), dtype=torch.float64, device=dev)
+    _abi.check(lib.mst_poly_derivative(_ptr(pp), count, ln, _ptr(out), _stream_ptr()), "mst_poly_derivative")
+    return out
+
+
+def poly_terms_at_t(p, t) -> torch.Tensor:
+    """``p[count, len]``, ``t[count]`` -> ``p[c, i] * t[c]**i``
+    (reference: Polynomial.pol_coeffs_at_t, src/optimizations/uav_trajectory.py:28-36)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    pp = _f64(p, dev)
+    if pp.dim() == 1:
+        pp = pp[None]
+    tt = _f64(t, dev).reshape(-1)
+    count, ln = pp.shape
+    out = torch.empty((count, ln), dtype=torch.float64, device=dev)
+    _abi.check(lib.mst_poly_terms_at_t(_ptr(pp), _ptr(tt), count, ln, _ptr(out), _stream_ptr()), "mst_poly_terms_at_t")
+    return out
+
+
 # --------------------------------------------------------------------------- a2-a4
 def solve_batch(wp, t, share_time_group: int = 1, solver: str = "auto"
                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -80,6 +109,21 @@ def solve_batch(wp, t, share_time_group: int = 1, solver: str = "auto"
                              _ptr(info), _ptr(ws), _stream_ptr())
     _abi.check(rc, "mst_solve_batch")
     return coef, dur, info
+
+
+# --------------------------------------------------------------------------- a8
+def pack_pol_matrix(coef, dur) -> torch.Tensor:
+    """``coef[B, n, K, 8]``, ``dur[B, n]`` -> float32 ``[B, n, 1 + 8K]`` rows
+    ``[T | x0..x7 | y0..y7 | ...]`` (reference: path_to_pol's matrix,
+    scripts/drones_pols_generator.py:63-77)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    coef = _f64(coef, dev)
+    dur = _f64(dur, dev)
+    B, n, K, _ = coef.shape
+    out = torch.empty((B, n, 1 + 8 * K), dtype=torch.float32, device=dev)
+    _abi.check(lib.mst_pack_pol_matrix(_ptr(coef), _ptr(dur), B, n, K, _ptr(out), _stream_ptr()), "mst_pack_pol_matrix")
+    return out
 
 
 # --------------------------------------------------------------------------- a5/a6

@@ -33,6 +33,9 @@ int launch_sample(const double* coef, const double* dur, int B, int n, int K, co
 int launch_flat(const double* coef, const double* dur, int B, int n, const double* ts, int ts_per_traj,
                 int S, int mode, double* out, uint8_t* status, cudaStream_t stream);
 int launch_time_power(const double* t, int count, double* rows, cudaStream_t stream);
+int launch_pack_matrix(const double* coef, const double* dur, long long rows, int K, float* out, cudaStream_t stream);
+int launch_poly_derivative(const double* p, int count, int len, double* out, cudaStream_t stream);
+int launch_poly_terms(const double* p, const double* t, int count, int len, double* out, cudaStream_t stream);
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream);
 int launch_any_hit(const uint8_t* hit, int B, int S, uint8_t* any_hit, cudaStream_t stream);
@@ -83,6 +86,28 @@ extern "C" const char* mst_last_cuda_error(void) { return g_cuda_error; }
 extern "C" int mst_time_power_rows(const double* t, int count, double* rows, void* stream) {
   if (count < 0 || (count > 0 && (!t || !rows))) return MST_ERR_INVALID;
   return launch_time_power(t, count, rows, (cudaStream_t)stream);
+}
+
+extern "C" int mst_poly_derivative(const double* p, int count, int len, double* out, void* stream) {
+  if (count < 0 || len < 1 || len > 64) return MST_ERR_INVALID;
+  if (count == 0 || len == 1) return MST_OK;
+  if (!p || !out) return MST_ERR_INVALID;
+  return launch_poly_derivative(p, count, len, out, (cudaStream_t)stream);
+}
+
+extern "C" int mst_poly_terms_at_t(const double* p, const double* t, int count, int len, double* out, void* stream) {
+  if (count < 0 || len < 1 || len > 64) return MST_ERR_INVALID;
+  if (count == 0) return MST_OK;
+  if (!p || !t || !out) return MST_ERR_INVALID;
+  return launch_poly_terms(p, t, count, len, out, (cudaStream_t)stream);
+}
+
+extern "C" int mst_pack_pol_matrix(const double* coef, const double* dur, int B, int n, int K, float* out,
+                                   void* stream) {
+  if (B < 0 || n < 1 || K < 1) return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!coef || !dur || !out) return MST_ERR_INVALID;
+  return launch_pack_matrix(coef, dur, (long long)B * n, K, out, (cudaStream_t)stream);
 }
 
 extern "C" size_t mst_solve_workspace_bytes(int B, int n, int K, int share_time_group) {

@@ -11,6 +11,21 @@
 
 namespace mst {
 
+// x^e (small e >= 0) rounded once: the power is carried as an unevaluated sum hi + lo
+// (FMA error-free products), so the result is the correctly rounded power in all but
+// astronomically rare cases — what Python's float ** int (libm pow) returns.
+__device__ __forceinline__ double pow_rounded_once(double x, int e) {
+  double hi = 1.0, lo = 0.0;
+  for (int i = 0; i < e; ++i) {
+    const double p = __dmul_rn(hi, x);
+    const double err = __fma_rn(hi, x, -p);
+    const double l = __fma_rn(lo, x, err);
+    hi = __dadd_rn(p, l);
+    lo = __dadd_rn(__dsub_rn(p, hi), l);
+  }
+  return hi;
+}
+
 // one Polynomial.derivative step on c[0..len-1]: c[i] = (i+1) * c[i+1]; returns len-1
 __device__ __forceinline__ int derive_once(double* c, int len) {
   for (int i = 0; i + 1 < len; ++i) c[i] = __dmul_rn((double)(i + 1), c[i + 1]);
@@ -155,27 +170,66 @@ flat_kernel(const double* __restrict__ coef, const double* __restrict__ dur, lon
   }
 }
 
-// x^e (0 <= e <= 7) rounded once: the power is carried as an unevaluated sum hi + lo
-// (FMA error-free products), so the result is the correctly rounded power in all but
-// astronomically rare cases — what Python's float ** int (libm pow) returns.
-__device__ __forceinline__ double pow_rounded_once(double x, int e) {
-  double hi = 1.0, lo = 0.0;
-  for (int i = 0; i < e; ++i) {
-    const double p = __dmul_rn(hi, x);
-    const double err = __fma_rn(hi, x, -p);
-    const double l = __fma_rn(lo, x, err);
-    hi = __dadd_rn(p, l);
-    lo = __dadd_rn(__dsub_rn(p, hi), l);
-  }
-  return hi;
-}
-
 // rows[count][8][8]: derivative j, power k -> k!/(k-j)! * t^(k-j)
 __global__ void time_power_kernel(const double* __restrict__ t, int count, double* __restrict__ rows) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count * 64) return;
   const int a = idx >> 6, j = (idx >> 3) & 7, k = idx & 7;
   rows[idx] = (k >= j) ? __dmul_rn(falling_factorial(k, j), pow_rounded_once(t[a], k - j)) : 0.0;
+}
+
+// Polynomial.derivative for `count` polynomials of `len` coefficients each:
+// out[c][i] = (i+1) * p[c][i+1], i < len-1   (uav_trajectory.py:25-26)
+__global__ void poly_derivative_kernel(const double* __restrict__ p, int count, int len, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * (len - 1)) return;
+  const int c = idx / (len - 1), i = idx - c * (len - 1);
+  out[idx] = __dmul_rn((double)(i + 1), p[c * len + i + 1]);
+}
+
+// Polynomial.pol_coeffs_at_t: out[c][i] = p[c][i] * t[c]**i   (uav_trajectory.py:28-36)
+__global__ void poly_terms_kernel(const double* __restrict__ p, const double* __restrict__ t, int count, int len,
+                                  double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * len) return;
+  const int c = idx / len, i = idx - c * len;
+  out[idx] = __dmul_rn(p[idx], pow_rounded_once(t[c], i));
+}
+
+int launch_poly_derivative(const double* p, int count, int len, double* out, cudaStream_t stream) {
+  const int total = count * (len - 1);
+  if (total <= 0) return MST_OK;
+  poly_derivative_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p, count, len, out);
+  return check_launch();
+}
+
+int launch_poly_terms(const double* p, const double* t, int count, int len, double* out, cudaStream_t stream) {
+  const int total = count * len;
+  if (total <= 0) return MST_OK;
+  poly_terms_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p, t, count, len, out);
+  return check_launch();
+}
+
+// (n, 1 + 8K) float32 rows [T | x0..x7 | y0..y7 | ...] of path_to_pol
+// (scripts/drones_pols_generator.py:63-77), one thread per output element
+__global__ void pack_matrix_kernel(const double* __restrict__ coef, const double* __restrict__ dur, long long rows,
+                                   int K, float* __restrict__ out) {
+  const int width = 1 + MST_NCOEF * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < rows * width;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / width;
+    const int col = (int)(idx - row * width);
+    out[idx] = (float)(col == 0 ? dur[row] : coef[row * (width - 1) + col - 1]);
+  }
+}
+
+int launch_pack_matrix(const double* coef, const double* dur, long long rows, int K, float* out, cudaStream_t stream) {
+  if (rows <= 0) return MST_OK;
+  const long long total = rows * (1 + MST_NCOEF * K);
+  long long g = (total + 255) / 256;
+  if (g > (long long)MST_SM_COUNT * 32) g = (long long)MST_SM_COUNT * 32;
+  pack_matrix_kernel<<<(unsigned)g, 256, 0, stream>>>(coef, dur, rows, K, out);
+  return check_launch();
 }
 
 static unsigned grid_for(long long total, int block) {

@@ -1,0 +1,99 @@
+"""B200 drop-in for ``RigidBodyPlanners.fcl_checker``
+(reference: src/RigidBodyPlanners/fcl_checker.py).
+
+``Fcl_mesh`` / ``Fcl_checker`` keep the reference's constructor arguments, attributes
+(``verts``, ``vecs``, ``tris``, ``collision_object``) and methods, so
+``PlannerSepCollision.isStateValid`` (RB_planning_sep_coll_check.py:208-226) runs unchanged —
+but there is no python-fcl underneath: the meshes live on the GPU and every query is answered
+by ``mst_collide_poses``.  ``check_collision_batch`` is the extra, batched entry point (all
+interpolated states of a motion in one launch).
+"""
+import numpy as np
+
+import drone_path_planning_python_b200 as _mst
+from drone_path_planning_python_b200 import meshio as _meshio
+
+
+class Fcl_mesh():
+    """reference: fcl_checker.py:13-59"""
+
+    def __init__(self, filename) -> None:
+        self.load_stl(filename)
+        self.create_indexed_triangles(self.verts, self.vecs)
+        self.create_fcl_mesh()
+
+    def load_stl(self, filename):
+        # unique vertices and corners, both rounded to 2 decimals in float32 (:20-23)
+        vectors = _meshio.read_stl(filename)
+        verts, vecs, _ = _meshio.ingest_mesh(vectors)
+        self.verts, self.vecs = verts, vecs
+        return verts, vecs
+
+    def create_indexed_triangles(self, vertices, vectors):
+        """Indexed triangle mesh from a vertex table and the triangle corners (:28-40)."""
+        tris = np.zeros([len(vectors), 3])
+        for i, tri in enumerate(vectors):
+            for j, corner in enumerate(tri):
+                match = np.flatnonzero(np.all(corner == vertices, axis=1))
+                if match.size != 1:
+                    raise ValueError("setting an array element with a sequence.")  # what numpy raises in the reference
+                tris[i][j] = match[0]
+        self.tris = tris
+        return tris
+
+    def create_fcl_mesh(self):
+        """Upload the mesh; the returned object plays the role of fcl.BVHModel (:42-52)."""
+        soup = _meshio.triangle_soup(self.verts, self.tris)
+        self.m = _mst.Mesh(soup)
+        self.T = np.zeros(3)
+        self.q = np.array([0.0, 0.0, 0.0, 1.0])
+        self.collision_object = self
+        return self.m
+
+    def set_transform(self, T=[0, 0, 0], q=[0, 0, 0, 1]):
+        # q arrives as xyzw like in the reference, which reorders it for fcl (:54-59)
+        self.T = np.asarray(T, dtype=np.float64).reshape(3)
+        self.q = np.asarray(q, dtype=np.float64).reshape(4)
+
+    def pose(self):
+        return np.concatenate([self.T, self.q])
+
+
+def visualize_meshes(filenames):
+    """Plot STL files (reference :62-82); matplotlib imported lazily."""
+    from matplotlib import pyplot as plt
+    from mpl_toolkits import mplot3d
+
+    figure = plt.figure()
+    axes = mplot3d.Axes3D(figure)
+    for filename in filenames:
+        axes.add_collection3d(mplot3d.art3d.Poly3DCollection(_meshio.read_stl(filename)))
+    axes.set_xlabel('X')
+    axes.set_ylabel('Y')
+    axes.set_zlabel('Z')
+    plt.show()
+
+
+class Fcl_checker():
+    """reference: fcl_checker.py:85-103"""
+
+    def __init__(self, env_mesh_file, robot_mesh_file) -> None:
+        self.env = Fcl_mesh(env_mesh_file)
+        self.robot = Fcl_mesh(robot_mesh_file)
+        self.request = None   # fcl.CollisionRequest() in the reference: default request, no contacts
+        self.result = None
+
+    def check_collision(self, T=None, q=[0, 0, 0, 1]):
+        if T is not None:
+            self.robot.set_transform(T, q)
+        hit = _mst.collide_poses(self.robot.m, self.env.m, self.robot.pose()[None, :])
+        # fcl.collide returns the number of contacts: 0 or 1 for the default request
+        return int(hit[0])
+
+    def set_robot_transform(self, T, q=[0, 0, 0, 1]):
+        self.robot.set_transform(T, q)
+
+    def check_collision_batch(self, poses):
+        """``poses[P, 4]`` (x, y, z, yaw — ``isStateValid``'s state) or ``[P, 7]``
+        (x, y, z, qx, qy, qz, qw) -> uint8 numpy array of collision flags, one launch."""
+        return _mst.collide_poses(self.robot.m, self.env.m, np.asarray(poses, dtype=np.float64)).cpu().numpy()

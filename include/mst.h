@@ -85,6 +85,18 @@ const char* mst_last_cuda_error(void);
 int mst_time_power_rows(const double* t, int count, double* rows, void* stream);
 
 /*
+ * Polynomial.derivative (src/optimizations/uav_trajectory.py:25-26) for `count` polynomials
+ * of `len` ascending coefficients:  p[count][len] -> out[count][len-1], out[i] = (i+1)*p[i+1].
+ */
+int mst_poly_derivative(const double* p, int count, int len, double* out, void* stream);
+
+/*
+ * Polynomial.pol_coeffs_at_t (src/optimizations/uav_trajectory.py:28-36):
+ *   p[count][len], t[count] -> out[count][len], out[c][i] = p[c][i] * t[c]**i
+ */
+int mst_poly_terms_at_t(const double* p, const double* t, int count, int len, double* out, void* stream);
+
+/*
  * Batched minimum-snap solve — calculate_trajectory1D / calculate_trajectory4D
  * (src/optimizations/calculatingTrajectories.py:37-213): for every trajectory the
  * 8n x 8n interpolation + C^1..C^6 continuity + rest-to-rest system is solved for
@@ -103,6 +115,15 @@ size_t mst_solve_workspace_bytes(int B, int n, int K, int share_time_group);
 int mst_solve_batch(const double* wp, const double* t, int B, int n, int K,
                     int share_time_group, int solver, double* coef, double* dur,
                     int* info, void* workspace, void* stream);
+
+/*
+ * Polynomial-piece matrix — the wire format path_to_pol writes to CSV and publishes
+ * (scripts/drones_pols_generator.py:63-87): per piece one float32 row
+ * [T | x0..x7 | y0..y7 | z0..z7 | yaw0..yaw7].
+ *   coef [B][n][K][8], dur [B][n]  ->  out [B][n][1 + 8K] float32
+ */
+int mst_pack_pol_matrix(const double* coef, const double* dur, int B, int n, int K, float* out,
+                        void* stream);
 
 /*
  * Batched evaluation — Polynomial.eval / Polynomial.derivative /

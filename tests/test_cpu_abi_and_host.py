@@ -1,0 +1,217 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/mst.h declares, argument
+validation works without a GPU, host-side logic (mesh IO, sharding plan), the kernels'
+__host__ __device__ arithmetic compiled for the host (tests/hostcheck) against the oracle, and
+the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from drone_path_planning_python_b200 import _abi, build
+    build.build_library()
+    return _abi.load()
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _lib()
+    header = open(os.path.join(ROOT, "include", "mst.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(mst_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    from drone_path_planning_python_b200 import _abi
+    assert declared == set(_abi.PROTOTYPES), declared ^ set(_abi.PROTOTYPES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib()
+    assert lib.mst_version() == 100
+    assert lib.mst_strerror(0) == b"ok" and lib.mst_strerror(-2).startswith(b"problem does not fit")
+    # invalid arguments are rejected before any CUDA call
+    assert lib.mst_solve_batch(None, None, 4, 0, 3, 1, 0, None, None, None, None, None) == -1   # n < 1
+    assert lib.mst_solve_batch(None, None, 5, 10, 3, 2, 0, None, None, None, None, None) == -1  # B % G
+    assert lib.mst_solve_batch(None, None, 4, 10, 3, 1, 9, None, None, None, None, None) == -1  # solver id
+    assert lib.mst_solve_batch(None, None, 0, 10, 3, 1, 0, None, None, None, None, None) == 0   # empty batch
+    assert lib.mst_sample_batch(None, None, 1, 1, 1, None, 0, 4, 7, 0, None, None, None) == -1  # mode
+    assert lib.mst_collide_poses(None, None, None, 1, 4, None, None) == -1
+    assert lib.mst_formation_waypoints(None, 1, 2, 5, None, 1, 3, None, None) == -1             # pose_dim
+    assert lib.mst_pipeline_launch_count(1 << 20, 10, 3, 1, 0, 100) == 3
+    assert lib.mst_solve_workspace_bytes(1024, 10, 3, 1) >= 4 * 1024
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import drone_path_planning_python_b200 as mst
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mst.solve_batch(np.zeros((1, 3, 3)), np.array([[0.0, 1.0, 2.0]]))
+    sys.path.insert(0, mst.dropin_path())
+    try:
+        import optimizations
+        pts = [optimizations.Point_time(optimizations.Waypoint(i, 0, 0, 0), t=i) for i in range(3)]
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            optimizations.calculate_trajectory4D(pts)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            optimizations.Polynomial([1.0, 2.0]).eval(0.5)
+    finally:
+        sys.path.remove(mst.dropin_path())
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing in the shipped package may import, load or even
+    name it."""
+    pkg = os.path.join(ROOT, "drone_path_planning_python_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), (dirpath, f)
+
+
+def test_stl_roundtrip_and_ingest(tmp_path):
+    from drone_path_planning_python_b200 import meshio
+    for name in ("custom_triangle_robot", "env-scene-hole"):
+        raw = meshio.shipped_mesh(name)
+        path = tmp_path / (name + ".stl")
+        meshio.write_stl(str(path), raw)
+        assert np.array_equal(meshio.read_stl(str(path)), raw)
+        verts, vecs, tris = meshio.ingest_mesh(raw)
+        assert tris.dtype == np.float64 and vecs.dtype == np.float32
+        assert np.array_equal(meshio.triangle_soup(verts, tris), vecs.astype(np.float64))
+    ascii_path = tmp_path / "a.stl"
+    ascii_path.write_text("solid a\nfacet normal 0 0 1\nouter loop\nvertex 0 0 0\nvertex 1 0 0\nvertex 0 1 0\n"
+                          "endloop\nendfacet\nendsolid a\n")
+    assert meshio.read_stl(str(ascii_path)).shape == (1, 3, 3)
+
+
+def test_shard_bounds_and_chunk_plan():
+    from drone_path_planning_python_b200.distributed import chunk_plan, shard_bounds
+    for total, world, group in [(1 << 20, 8, 1), (20480, 8, 5), (35, 4, 5), (7, 3, 1)]:
+        covered = []
+        for r in range(world):
+            lo, hi = shard_bounds(total, world, r, group)
+            assert lo % group == 0 and hi % group == 0
+            covered += list(range(lo, hi))
+        assert covered == list(range(total))
+    plan = chunk_plan(1000, 8, 5)
+    assert plan[0][0] == 0 and plan[-1][1] == 1000 and all((b - a) % 5 == 0 for a, b in plan)
+    assert chunk_plan(3, 8) == [(0, 1), (1, 2), (2, 3)]
+
+
+# ------------------------------------------------------------------ host build of the kernels' arithmetic
+def _hostcheck():
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cu")
+    out = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
+    csrc = os.path.join(ROOT, "drone_path_planning_python_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc))
+    if not os.path.exists(out) or os.path.getmtime(out) < max(newest, os.path.getmtime(src)):
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "--extended-lambda", "-Wno-deprecated-gpu-targets",
+                        "-Xcompiler", "-fPIC", "-shared", "-o", out, src], check=True, capture_output=True)
+    return ctypes.CDLL(out)
+
+
+P = ctypes.c_void_p
+
+
+@pytest.mark.parametrize("n,K", [(1, 3), (2, 4), (10, 3), (10, 4), (20, 3)])
+def test_condensed_core_matches_oracle(n, K):
+    from oracle import minsnap_oracle as mo
+    lib = _hostcheck()
+    rng = np.random.default_rng(100 * n + K)
+    B = 24
+    T = rng.uniform(0.5, 2.0, (B, n))
+    t = np.ascontiguousarray(np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1))
+    wp = np.ascontiguousarray(np.cumsum(rng.normal(0, 0.3, (B, n + 1, K)), axis=1) + rng.uniform(-2, 2, (B, 1, K)))
+    coef = np.full((B, n, K, 8), np.nan)
+    cls = np.zeros(B, np.int32)
+    assert lib.hostcheck_condensed(P(wp.ctypes.data), P(t.ctypes.data), B, n, K, 1, 0, P(coef.ctypes.data),
+                                   P(cls.ctypes.data)) == 0
+    assert (cls == 0).all()
+    for b in range(B):
+        ref, _ = mo.solve_waypoints(wp[b], t[b])
+        err = (np.abs(coef[b] - ref).max(axis=(0, 2)) / np.abs(ref).max(axis=(0, 2))).max()
+        assert err <= 1e-9, (b, err)
+
+
+def test_condensed_core_declines_what_it_cannot_reproduce():
+    lib = _hostcheck()
+    n, K = 6, 3
+    t = np.array([[0, 1, 2, 3, 4, 5, 6.0],        # fine
+                  [0, 1, 2, 3, 4, 5, 30.0],       # spread > 4 -> pivoted solver
+                  [0.5, 1, 2, 3, 4, 5, 6.0],      # t0 != 0 quirk
+                  [0, 1, 1, 3, 4, 5, 6.0],        # zero-length piece (singular)
+                  [0, 2, 1, 3, 4, 5, 6.0],        # decreasing
+                  [0, np.inf, 2, 3, 4, 5, 6.0]])
+    wp = np.zeros((6, n + 1, K))
+    coef = np.zeros((6, n, K, 8))
+    cls = np.zeros(6, np.int32)
+    lib.hostcheck_condensed(P(wp.ctypes.data), P(t.ctypes.data), 6, n, K, 1, 0, P(coef.ctypes.data), P(cls.ctypes.data))
+    assert cls.tolist() == [0, 1, 1, 1, 2, 3]
+
+
+def _soup(name):
+    from drone_path_planning_python_b200 import meshio
+    verts, _, tris = meshio.ingest_mesh(meshio.shipped_mesh(name))
+    return np.ascontiguousarray(meshio.triangle_soup(verts, tris))
+
+
+@pytest.mark.parametrize("robot_name", ["custom_triangle_robot", "robot-scene-triangle"])
+@pytest.mark.parametrize("env_name", ["env-scene-ltu-experiment", "env-scene-hole"])
+def test_culled_collision_routine_matches_oracle(robot_name, env_name):
+    from oracle import build_oracle, collision_oracle as co
+    lib = _hostcheck()
+    rng = np.random.default_rng(len(robot_name) * 100 + len(env_name))
+    robot, env = _soup(robot_name), _soup(env_name)
+    flat = env.reshape(-1, 3)
+    for dim in (3, 4, 7):
+        n = 4000
+        pos = rng.uniform(flat.min(0) - 0.8, flat.max(0) + 0.8, (n, 3))
+        if dim == 7:
+            q = rng.normal(size=(n, 4))
+            poses = np.concatenate([pos, q / np.linalg.norm(q, axis=1, keepdims=True)], axis=1)
+        else:
+            poses = np.concatenate([pos, rng.uniform(-np.pi, np.pi, (n, 1)) * (dim == 4)], axis=1)
+        ref = build_oracle.c_collide_poses(robot, env, poses)
+        R, T = co.pose_matrices(poses)
+        R, T = np.ascontiguousarray(R), np.ascontiguousarray(T)
+        hit = np.zeros(n, np.uint8)
+        V = lib.hostcheck_collide_culled(P(robot.ctypes.data), len(robot), P(env.ctypes.data), len(env),
+                                         P(R.ctypes.data), P(T.ctypes.data), n, int(dim != 3), int(dim != 7),
+                                         P(hit.ctypes.data))
+        assert V <= 8
+        assert np.array_equal(hit, ref), (dim, int((hit != ref).sum()))
+
+
+def test_interval_triangle_test_equals_sat_outside_the_touching_band():
+    from oracle import collision_oracle as co
+    lib = _hostcheck()
+    rng = np.random.default_rng(12)
+    N = 60000
+    sets = {
+        "random": rng.uniform(-1, 1, (N, 2, 3, 3)),
+        "clustered": rng.uniform(-1, 1, (N, 1, 1, 3)) + rng.normal(0, 0.3, (N, 2, 3, 3)),
+        "grid": np.round(rng.uniform(-1, 1, (N, 2, 3, 3)) * 4) / 4,
+        "nearly_coplanar": rng.uniform(-1, 1, (N, 2, 3, 3)) * np.array([1, 1, 1e-7]),
+        "coplanar": rng.uniform(-1, 1, (N, 2, 3, 3)) * np.array([1, 1, 0]),
+    }
+    deg = rng.uniform(-1, 1, (N, 2, 3, 3))
+    deg[:, 0, 2] = deg[:, 0, 1]
+    sets["degenerate"] = deg
+    for name, tri in sets.items():
+        tri = np.ascontiguousarray(tri)
+        o17, oi = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        lib.hostcheck_tri_pairs(P(tri.ctypes.data), N, P(o17.ctypes.data), P(oi.ctypes.data))
+        hit, gap = co.sat_pair(tri[:, 0], tri[:, 1])
+        assert np.array_equal(hit, o17.astype(bool)), name        # the kernels' SAT is the oracle's SAT
+        clear = np.abs(gap) > 1e-9
+        assert np.array_equal(o17[clear], oi[clear]), name
