@@ -198,6 +198,9 @@ def run_ours(args):
     from drone_path_planning_python_b200 import _abi
     from drone_path_planning_python_b200.host_pipeline import HostPipeline
 
+    # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, next to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
