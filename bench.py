@@ -228,22 +228,39 @@ def run_ours(args):
                              torch.empty((B, S_SAMPLES), dtype=torch.uint8, device=dev),
                              torch.empty((B,), dtype=torch.uint8, device=dev))
 
-    # multi-GPU: chunked all-gather of coefficients + flags, overlapped with the next chunk
-    from drone_path_planning_python_b200.distributed import ChunkedAllGather
-    gather = None
-    n_chunks = 1
+    # multi-GPU: all-gather of coefficients + flags, chunked and overlapped with the next chunk.
+    # Preferred: peer push over NVLink with the copy engines (distributed.PeerPushAllGather);
+    # fallback: NCCL all_gather_into_tensor (distributed.ChunkedAllGather).
+    from drone_path_planning_python_b200.distributed import ChunkedAllGather, PeerPushAllGather
+    gather, gather_kind, n_chunks = None, None, 1
     if world > 1:
-        gather = ChunkedAllGather(B, world, args.gather_chunks, [res.coef, res.hit, res.any_hit])
+        if args.gather == "push":
+            try:
+                gather = PeerPushAllGather(B, world, rank, args.gather_chunks, [res.coef, res.hit, res.any_hit])
+                gather_kind = "peer push over NVLink (copy engines, symmetric memory)"
+                res = mst.PipelineResult(gather.local_slot(0), res.dur, res.info, gather.local_slot(1),
+                                         gather.local_slot(2))
+            except Exception as exc:  # symmetric memory unavailable on this box
+                sys.stderr.write("peer-push gather unavailable (%r); using NCCL\n" % (exc,))
+                gather = None
+        if gather is None:
+            gather = ChunkedAllGather(B, world, args.gather_chunks, [res.coef, res.hit, res.any_hit])
+            gather_kind = "NCCL all_gather_into_tensor"
         n_chunks = len(gather.plan)
 
+    def chunk_view(lo, hi):
+        return mst.PipelineResult(res.coef[lo:hi], res.dur[lo:hi], res.info[lo:hi], res.hit[lo:hi], res.any_hit[lo:hi])
+
     def compute_chunk(lo, hi):
-        view = mst.PipelineResult(res.coef[lo:hi], res.dur[lo:hi], res.info[lo:hi], res.hit[lo:hi], res.any_hit[lo:hi])
+        view = chunk_view(lo, hi)
         mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
         return view.coef, view.hit, view.any_hit
 
     def step():
         if world == 1:
             mst.pipeline(wp, t, S_SAMPLES, robot, env, out=res)
+        elif isinstance(gather, PeerPushAllGather):
+            gather.run(compute_chunk)
         else:
             gather.run(compute_chunk, assemble=False)   # results stay in [chunk][rank][...] staging buffers
 
@@ -337,7 +354,7 @@ def run_ours(args):
                                % (B, N_SEG, K_AX, S_SAMPLES, ROBOT, ENV, SEED),
                    "trajectories_per_gpu": B, "l2": "inputs+outputs %.2f GB per step >> 126 MB L2 (no flush needed)"
                    % (B * (ALG_BYTES + N_SEG * 8 + 4) / 1e9),
-                   "gather": None if world == 1 else "NCCL all_gather of coef(f64)+hit+any_hit in %d chunks, overlapped" % n_chunks,
+                   "gather": None if world == 1 else "%s of coef(f64)+hit+any_hit, %d chunks" % (gather_kind, n_chunks),
                    "solver": "auto (condensed LDL^T; banded pivoted LU for wide duration spreads)"},
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -375,7 +392,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--traj", type=int, default=TRAJ_PER_GPU, help="trajectories per GPU per step")
-    ap.add_argument("--gather-chunks", type=int, default=8)
+    ap.add_argument("--gather-chunks", type=int, default=4)
+    ap.add_argument("--gather", choices=["push", "nccl"], default="push")
     ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="tiny CPU sample (smoke runs)")
