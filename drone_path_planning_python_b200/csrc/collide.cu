@@ -29,12 +29,15 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
                const double* __restrict__ pose, long long P, int pose_dim, uint8_t* __restrict__ hit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ unsigned work_queue[4][65];  // per warp: 64-entry ring + hit mask
+  __shared__ unsigned work_queue[4][COLLIDE_WQ_WORDS];  // per warp: item ring + hit mask
   unsigned* wq = work_queue[threadIdx.x >> 5];
   stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
   const MeshView rb = mesh_view(smem_raw, rl);
   const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
-  const bool culled = rb.V <= 64 && rb.T < 4096 && ev.T < 4096;
+  const bool culled = rb.V <= COLLIDE_MAX_V && rb.T < 4096 && ev.T < 4096;
+  double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);  // plane x vertex table
+  if (culled && pose_dim == 3) build_plane_vertex_table(rb, ev, nv);
+  __syncthreads();
   // warp-uniform trip count (the collision test votes across the warp)
   for (long long base = blockIdx.x * (long long)blockDim.x; base < P; base += (long long)gridDim.x * blockDim.x) {
     const long long idx = base + threadIdx.x;
@@ -44,7 +47,7 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
     if (pose_dim == 3) {
       const double pp[3] = {ps[0], ps[1], ps[2]};
       if (culled) {
-        h = robot_hits_env_queue<0>(active, pp, rb, rbb, ev, evb, wq);
+        h = robot_hits_env_queue<0>(active, pp, rb, rbb, ev, evb, nv, wq);
       } else {
         const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
@@ -53,7 +56,7 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
       double pp[5] = {ps[0], ps[1], ps[2], 0.0, 0.0};
       sincos(ps[3] * 0.5, &pp[3], &pp[4]);
       if (culled) {
-        h = robot_hits_env_queue<1>(active, pp, rb, rbb, ev, evb, wq);
+        h = robot_hits_env_queue<1>(active, pp, rb, rbb, ev, evb, nv, wq);
       } else {
         double R[9];
         quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
@@ -62,7 +65,7 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
     } else {
       const double pp[7] = {ps[0], ps[1], ps[2], ps[3], ps[4], ps[5], ps[6]};
       if (culled) {
-        h = robot_hits_env_queue<2>(active, pp, rb, rbb, ev, evb, wq);
+        h = robot_hits_env_queue<2>(active, pp, rb, rbb, ev, evb, nv, wq);
       } else {
         double R[9];
         quat_to_matrix(pp[3], pp[4], pp[5], pp[6], R);
@@ -89,8 +92,8 @@ __global__ void any_hit_kernel(const uint8_t* __restrict__ hit, int B, int S, ui
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;
-  const size_t smem = robot->layout.bytes + env->layout.bytes;
-  if (smem > MST_MAX_SMEM - 1024) return MST_ERR_TOO_LARGE;
+  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * (size_t)env->T * robot->V;
+  if (smem > MST_MAX_SMEM - 10240) return MST_ERR_TOO_LARGE;
   if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          MST_MAX_SMEM);

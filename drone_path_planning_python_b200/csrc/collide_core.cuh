@@ -244,18 +244,27 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
 // Warp-cooperative form of robot_hits_env_culled with WORK COMPACTION: lane <-> pose for the
 // broad phase, lane <-> (pose, robot triangle, env triangle) item for the narrow phase.
 //
-// A profile of the per-lane version (profiles/r1a_*) showed ~86 % of all issued
-// instructions inside the SAT with 4.5 of 32 lanes active: neighbouring poses survive the
-// culls with DIFFERENT triangle pairs, so the lanes serialise.  Here the broad phase
-// (bounding boxes, the env plane against all robot vertices, the vertex masks — the very
-// same predicates) only ENQUEUES surviving (lane, e, r) triples into a 64-entry ring in
-// shared memory, using warp ballots for the slots; whenever 32 items are waiting the warp
-// runs the SAT on 32 different items at once (the pose of the item's source lane comes by
-// shuffle), and a hit is OR-ed into a per-warp bit mask.  The pair test is the interval
-// form (triangles_intersect_interval), equal to the 17-axis SAT away from touching.
+// A profile of the per-lane version (profiles/r1_collision_history.md) showed ~86 % of all
+// issued instructions inside the SAT with 4.5 of 32 lanes active: neighbouring poses survive
+// the culls with DIFFERENT triangle pairs, so the lanes serialise.  Here the broad phase
+// (bounding boxes, the env plane against all robot vertices, the vertex masks — the very same
+// predicates) only ENQUEUES surviving (lane, e, r) triples into a ring in shared memory:
+// every lane collects the robot triangles it needs against env triangle e as a bit mask, one
+// warp prefix sum hands out the slots, and whenever 32 items are waiting the warp runs the
+// pair test on 32 different items at once (the pose of the item's source lane comes by
+// shuffle); a hit is OR-ed into a per-warp bit mask.  The pair test is the interval form
+// (triangles_intersect_interval), equal to the 17-axis SAT away from touching.
 //
 // POSE: 0 translation (x,y,z); 1 yaw (x,y,z,sin(yaw/2),cos(yaw/2)); 2 quaternion
-// (x,y,z,qx,qy,qz,qw).  wq: 65 unsigned of shared memory owned by this warp.
+// (x,y,z,qx,qy,qz,qw).  wq: COLLIDE_WQ_WORDS unsigned of shared memory owned by this warp.
+// nv (POSE 0 only): table nv[e][v] = n_e . v of plane normals against the robot's unique
+// vertices (build_plane_vertex_table) — a translation leaves it constant, so the signed
+// distance of vertex v to plane e is one add.
+constexpr int COLLIDE_RING = 512;                     // entries; a power of two
+constexpr int COLLIDE_RBLOCK = 15;                    // robot triangles enqueued per round: 31 + 32*15 <= 512
+constexpr int COLLIDE_WQ_WORDS = COLLIDE_RING + 1;    // + the per-warp hit mask
+constexpr int COLLIDE_MAX_V = 32;                     // unique robot vertices the bit masks can hold
+
 template <int POSE> struct PoseDim { static constexpr int N = POSE == 0 ? 3 : (POSE == 1 ? 5 : 7); };
 
 template <int POSE>
@@ -264,19 +273,29 @@ __device__ __forceinline__ void pose_rotation(const double* pp, double* R) {
   if (POSE == 2) quat_to_matrix(pp[3], pp[4], pp[5], pp[6], R);
 }
 
+// nv[e * V + v] = n_e . vertex_v ; every thread of the CTA calls it, followed by a CTA barrier
+__device__ __forceinline__ void build_plane_vertex_table(const MeshView& rb, const MeshView& ev, double* nv) {
+  for (int i = threadIdx.x; i < ev.T * rb.V; i += blockDim.x) {
+    const int e = i / rb.V, v = i - e * rb.V;
+    const double* pl = ev.plane + 4 * e;
+    const double* p = rb.vert + 3 * v;
+    nv[i] = pl[0] * p[0] + pl[1] * p[1] + pl[2] * p[2];
+  }
+}
+
 template <int POSE>
 __device__ __forceinline__ void narrow_phase_items(int count, unsigned head, const double* pp, const MeshView& rb,
                                                    const MeshView& ev, unsigned* wq) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const bool valid = lane < count;
-  const unsigned item = valid ? wq[(head + lane) & 63u] : 0u;
+  const unsigned item = valid ? wq[(head + lane) & (COLLIDE_RING - 1)] : 0u;
   const int src = valid ? (int)(item >> 24) : lane;
   const int e = (int)((item >> 12) & 0xfffu), r = (int)(item & 0xfffu);
   double q[PoseDim<POSE>::N];
 #pragma unroll
   for (int i = 0; i < PoseDim<POSE>::N; ++i) q[i] = __shfl_sync(FULL, pp[i], src);
-  if (valid && !((wq[64] >> src) & 1u)) {
+  if (valid && !((wq[COLLIDE_RING] >> src) & 1u)) {
     const double* pr = rb.tri + 9 * r;
     V3 P1, P2, P3;
     if (POSE == 0) {
@@ -294,16 +313,48 @@ __device__ __forceinline__ void narrow_phase_items(int count, unsigned head, con
           fmax(fmax(P1.z, P2.z), P3.z) < bx[2] || fmin(fmin(P1.z, P2.z), P3.z) > bx[5])) {
       const double* qe = ev.tri + 9 * e;
       const V3 Q1 = {qe[0], qe[1], qe[2]}, Q2 = {qe[3], qe[4], qe[5]}, Q3 = {qe[6], qe[7], qe[8]};
-      if (triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3)) atomicOr(&wq[64], 1u << src);
+      if (triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3)) atomicOr(&wq[COLLIDE_RING], 1u << src);
     }
   }
   __syncwarp();
 }
 
+// lane-local: can the robot at this pose touch the environment's root box at all?
+// (bounding sphere for rigid poses, then the robot's world box) — the first two culls of
+// robot_hits_env_queue, exposed so callers can compact the surviving poses first
+template <int POSE>
+__device__ __forceinline__ bool pose_near_environment(const double* pp, const MeshBounds& rbb, const MeshBounds& evb) {
+  const double* root = evb.root;
+  const double* T = pp;
+  if (POSE != 2 && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
+                    T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
+    return false;
+  double lo0, lo1, lo2, hi0, hi1, hi2;
+  if (POSE == 0) {
+    lo0 = rbb.root[0] + T[0]; lo1 = rbb.root[1] + T[1]; lo2 = rbb.root[2] + T[2];
+    hi0 = rbb.root[3] + T[0]; hi1 = rbb.root[4] + T[1]; hi2 = rbb.root[5] + T[2];
+  } else {
+    double R[9];
+    pose_rotation<POSE>(pp, R);
+    const double c0 = 0.5 * (rbb.root[0] + rbb.root[3]), c1 = 0.5 * (rbb.root[1] + rbb.root[4]),
+                 c2 = 0.5 * (rbb.root[2] + rbb.root[5]);
+    const double h0 = 0.5 * (rbb.root[3] - rbb.root[0]), h1 = 0.5 * (rbb.root[4] - rbb.root[1]),
+                 h2 = 0.5 * (rbb.root[5] - rbb.root[2]);
+    const double pad = 1e-12 * (rbb.radius + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
+    const double w0 = R[0] * c0 + R[1] * c1 + R[2] * c2 + T[0], w1 = R[3] * c0 + R[4] * c1 + R[5] * c2 + T[1],
+                 w2 = R[6] * c0 + R[7] * c1 + R[8] * c2 + T[2];
+    const double e0 = fabs(R[0]) * h0 + fabs(R[1]) * h1 + fabs(R[2]) * h2 + pad,
+                 e1 = fabs(R[3]) * h0 + fabs(R[4]) * h1 + fabs(R[5]) * h2 + pad,
+                 e2 = fabs(R[6]) * h0 + fabs(R[7]) * h1 + fabs(R[8]) * h2 + pad;
+    lo0 = w0 - e0; hi0 = w0 + e0; lo1 = w1 - e1; hi1 = w1 + e1; lo2 = w2 - e2; hi2 = w2 + e2;
+  }
+  return !(hi0 < root[0] || lo0 > root[3] || hi1 < root[1] || lo1 > root[4] || hi2 < root[2] || lo2 > root[5]);
+}
+
 template <int POSE>
 __device__ __forceinline__ bool robot_hits_env_queue(bool active, const double* pp, const MeshView& rb,
                                                      const MeshBounds& rbb, const MeshView& ev,
-                                                     const MeshBounds& evb, unsigned* wq) {
+                                                     const MeshBounds& evb, const double* nv, unsigned* wq) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const double* root = evb.root;
@@ -336,49 +387,75 @@ __device__ __forceinline__ bool robot_hits_env_queue(bool active, const double* 
   if (hi0 < root[0] || lo0 > root[3] || hi1 < root[1] || lo1 > root[4] || hi2 < root[2] || lo2 > root[5])
     near = false;
   if (!__any_sync(FULL, near)) return false;
-  if (lane == 0) wq[64] = 0u;
+  if (lane == 0) wq[COLLIDE_RING] = 0u;
   __syncwarp();
   unsigned head = 0u, tail = 0u;  // ring positions (warp-uniform)
-  const unsigned long long all = rb.V >= 64 ? ~0ull : ((1ull << rb.V) - 1ull);
-  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned all = rb.V >= 32 ? ~0u : ((1u << rb.V) - 1u);
   for (int e = 0; e < ev.T; ++e) {
     const double* bx = ev.box + 6 * e;
     bool pass = near && !(hi0 < bx[0] || lo0 > bx[3] || hi1 < bx[1] || lo1 > bx[4] || hi2 < bx[2] || lo2 > bx[5]);
     if (!__any_sync(FULL, pass)) continue;
-    unsigned long long above = 0ull, below = 0ull;
+    unsigned above = 0u, below = 0u;
     if (pass) {
       const double* pl = ev.plane + 4 * e;
-      double m0, m1, m2;
-      if (POSE != 0) {
-        m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
-        m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
-        m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
-      } else {
-        m0 = pl[0]; m1 = pl[1]; m2 = pl[2];
-      }
       const double off = pl[0] * T[0] + pl[1] * T[1] + pl[2] * T[2] - pl[3];
-      for (int v = 0; v < rb.V; ++v) {
-        const double* p = rb.vert + 3 * v;
-        const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
-        above |= (unsigned long long)(dist > 0.0) << v;
-        below |= (unsigned long long)(dist < 0.0) << v;
+      if (POSE == 0) {
+        const double* row = nv + e * rb.V;
+        for (int v = 0; v < rb.V; ++v) {
+          const double dist = row[v] + off;
+          above |= (unsigned)(dist > 0.0) << v;
+          below |= (unsigned)(dist < 0.0) << v;
+        }
+      } else {
+        // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
+        const double m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
+        const double m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
+        const double m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
+        for (int v = 0; v < rb.V; ++v) {
+          const double* p = rb.vert + 3 * v;
+          const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
+          above |= (unsigned)(dist > 0.0) << v;
+          below |= (unsigned)(dist < 0.0) << v;
+        }
       }
       if (above == all || below == all) pass = false;
     }
     if (!__any_sync(FULL, pass)) continue;
-    for (int r = 0; r < rb.T; ++r) {
-      const unsigned long long mk = rb.mask[r];
-      const bool need = pass && !((above & mk) == mk || (below & mk) == mk);
-      const unsigned vote = __ballot_sync(FULL, need);
-      if (!vote) continue;
-      if (need) wq[(tail + __popc(vote & lt_mask)) & 63u] = ((unsigned)lane << 24) | ((unsigned)e << 12) | (unsigned)r;
-      tail += __popc(vote);
+    for (int r0 = 0; r0 < rb.T; r0 += COLLIDE_RBLOCK) {
+      const int rn = min(COLLIDE_RBLOCK, rb.T - r0);
+      unsigned need = 0u;  // bit j: robot triangle r0+j has corners on both sides of (or on) plane e
+      if (pass) {
+        for (int j = 0; j < rn; ++j) {
+          const unsigned mk = (unsigned)rb.mask[r0 + j];
+          need |= (unsigned)(!((above & mk) == mk || (below & mk) == mk)) << j;
+        }
+      }
+      // slots: exclusive prefix sum of the per-lane counts
+      const int cnt = __popc(need);
+      int inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += up;
+      }
+      const int total = __shfl_sync(FULL, inc, 31);
+      if (total == 0) continue;
+      unsigned slot = tail + (unsigned)(inc - cnt);
+      while (need) {
+        const int j = __ffs(need) - 1;
+        need &= need - 1u;
+        wq[slot & (COLLIDE_RING - 1)] = ((unsigned)lane << 24) | ((unsigned)e << 12) | (unsigned)(r0 + j);
+        ++slot;
+      }
+      tail += (unsigned)total;
       if (tail - head >= 32u) {
         __syncwarp();
-        narrow_phase_items<POSE>(32, head, pp, rb, ev, wq);
-        head += 32u;
+        do {
+          narrow_phase_items<POSE>(32, head, pp, rb, ev, wq);
+          head += 32u;
+        } while (tail - head >= 32u);
         // poses already known to collide stop producing work
-        if ((wq[64] >> lane) & 1u) near = false;
+        if ((wq[COLLIDE_RING] >> lane) & 1u) near = false;
         pass = pass && near;
       }
     }
@@ -386,7 +463,7 @@ __device__ __forceinline__ bool robot_hits_env_queue(bool active, const double* 
   }
   __syncwarp();
   if (tail != head) narrow_phase_items<POSE>((int)(tail - head), head, pp, rb, ev, wq);
-  return active && ((wq[64] >> lane) & 1u);
+  return active && ((wq[COLLIDE_RING] >> lane) & 1u);
 }
 #endif  // __CUDACC__
 

@@ -26,31 +26,73 @@ namespace mst {
 
 constexpr int FUSED_THREADS = 128;
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
-constexpr int FUSED_WT = 4;  // trajectories per warp tile
+constexpr int FUSED_WT = 4;     // trajectories per warp tile
+constexpr int FUSED_NEAR = 64;  // ring of samples waiting for the collision test, per warp
+
+// per-warp shared memory of the fused kernel
+template <int NP>
+struct NearRing {
+  double pose[FUSED_NEAR][NP];  // x, y, z (, sin(yaw/2), cos(yaw/2))
+  int traj[FUSED_NEAR];
+  int sample[FUSED_NEAR];
+};
 
 // Every WARP walks its own tiles of FUSED_WT trajectories (no CTA-wide barrier after the
 // meshes are staged): a warp that meets the obstacle takes several times longer over a
 // tile than one that flies in free space, and a CTA barrier per tile made the fast warps
-// wait (27 % of all warp-stall samples in profiles/r1b).
+// wait (27 % of all warp-stall samples in profiles/r1_collision_history.md).
+//
+// Sampling and collision are decoupled inside the warp: every lane evaluates its sample and
+// applies the root-box cull; samples that fail it get hit = 0 right away, the others are
+// appended (ballot-compacted) to a ring of "near" samples, and only when 32 of them are
+// waiting does the warp run the collision test — on a DENSE batch, whatever mix of near and
+// far samples the trajectories produce.
 template <int K>
 __global__ void __launch_bounds__(FUSED_THREADS, 4)
 sample_collide_kernel(const double* __restrict__ coef, const double* __restrict__ dur, int B, int n, int S,
                       const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
                       const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
                       uint8_t* __restrict__ hit, uint8_t* __restrict__ any_hit) {
+  constexpr int POSE = K == 3 ? 0 : 1;
+  constexpr int NP = PoseDim<POSE>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ int any_flag[FUSED_WARPS][FUSED_WT];
-  __shared__ unsigned work_queue[FUSED_WARPS][65];  // per warp: 64-entry ring + hit mask
+  __shared__ unsigned work_queue[FUSED_WARPS][COLLIDE_WQ_WORDS];  // per warp: item ring + hit mask
+  __shared__ NearRing<NP> near_ring[FUSED_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned* wq = work_queue[warp];
+  NearRing<NP>& ring = near_ring[warp];
   stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
   const MeshView rb = mesh_view(smem_raw, rl);
   const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
-  const bool culled = rb.V <= 64 && rb.T < 4096 && ev.T < 4096;
-  // per-warp tables behind the meshes: knots[WT][n+1] (running sums), dt[WT]
-  double* knots = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes) + warp * FUSED_WT * (n + 2);
+  const bool culled = rb.V <= COLLIDE_MAX_V && rb.T < 4096 && ev.T < 4096;
+  // behind the meshes: the plane x vertex table, then per-warp tables knots[WT][n+1]
+  // (running sums of the durations) and dt[WT]
+  double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
+  if (culled && K == 3) build_plane_vertex_table(rb, ev, nv);
+  __syncthreads();
+  double* knots = nv + (culled ? ev.T * rb.V : 0) + warp * FUSED_WT * (n + 2);
   double* dts = knots + FUSED_WT * (n + 1);
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned ring_head = 0u, ring_tail = 0u;  // warp-uniform
+
+  // collision test of `count` waiting samples (lane <-> ring entry)
+  auto drain = [&](int count) {
+    const bool valid = lane < count;
+    const unsigned slot = (ring_head + (valid ? lane : 0)) & (FUSED_NEAR - 1);
+    double pp[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pp[i] = ring.pose[slot][i];
+    const int b = ring.traj[slot], s = ring.sample[slot];
+    const bool h = robot_hits_env_queue<POSE>(valid, pp, rb, rbb, ev, evb, nv, wq);
+    if (valid) {
+      hit[(size_t)b * S + s] = h ? 1 : 0;
+      if (h) any_hit[b] = 1;  // zeroed at the start of the trajectory's tile; every writer stores 1
+    }
+    ring_head += (unsigned)count;
+    __syncwarp();
+  };
 
   const int tiles = (B + FUSED_WT - 1) / FUSED_WT;
   for (int tile = blockIdx.x * FUSED_WARPS + warp; tile < tiles; tile += gridDim.x * FUSED_WARPS) {
@@ -64,12 +106,12 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       kn[0] = 0.0;
       for (int i = 0; i < n; ++i) { acc = __dadd_rn(acc, T[i]); kn[i + 1] = acc; }
       dts[lane] = __ddiv_rn(acc, (double)S);
-      any_flag[warp][lane] = 0;
+      any_hit[b0 + lane] = 0;
     }
     __syncwarp();
     const int work = nb * S;
-    // warp-uniform trip count: every lane stays in the loop (the collision test votes
-    // across the warp), lanes past the end of the tile are simply inactive
+    // warp-uniform trip count: every lane stays in the loop (ballots), lanes past the end of
+    // the tile are simply inactive
     for (int base = 0; base < work; base += 32) {
       const int idx = base + lane;
       const bool active = idx < work;
@@ -100,41 +142,46 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
         x = __dadd_rn(__dmul_rn(x, local), c01.x);
         pos[k] = x;
       }
-      bool h;
-      if (K == 3) {
-        if (culled) {
-          h = robot_hits_env_queue<0>(active, pos, rb, rbb, ev, evb, wq);
-        } else {
-          const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-          h = active && robot_hits_env(R, pos, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+      double pp[NP];
+      pp[0] = pos[0]; pp[1] = pos[1]; pp[2] = pos[2];
+      if (POSE == 1) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
+      if (!culled) {  // meshes the bit-mask culls cannot hold: plain per-lane test
+        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (POSE == 1) quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
+        if (active) {
+          const bool h = robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
+          hit[(size_t)b0 * S + idx] = h ? 1 : 0;
+          if (h) any_hit[b0 + tl] = 1;
         }
-      } else {
-        double pp[5] = {pos[0], pos[1], pos[2], 0.0, 0.0};
-        sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
-        if (culled) {
-          h = robot_hits_env_queue<1>(active, pp, rb, rbb, ev, evb, wq);
-        } else {
-          double R[9];
-          quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
-          h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
-        }
+        continue;
       }
-      if (active) {
-        hit[(size_t)b0 * S + idx] = h ? 1 : 0;
-        if (h) any_flag[warp][tl] = 1;  // benign race: every writer stores 1
+      const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
+      if (active && !near) hit[(size_t)b0 * S + idx] = 0;
+      const unsigned vote = __ballot_sync(FULL, near);
+      if (vote) {
+        if (near) {
+          const unsigned slot = (ring_tail + __popc(vote & lt_mask)) & (FUSED_NEAR - 1);
+#pragma unroll
+          for (int i = 0; i < NP; ++i) ring.pose[slot][i] = pp[i];
+          ring.traj[slot] = b0 + tl;
+          ring.sample[slot] = s;
+        }
+        ring_tail += __popc(vote);
+        __syncwarp();
+        if (ring_tail - ring_head >= 32u) drain(32);
       }
     }
-    __syncwarp();
-    if (lane < nb) any_hit[b0 + lane] = any_flag[warp][lane] ? 1 : 0;
   }
+  if (ring_tail != ring_head) drain((int)(ring_tail - ring_head));
 }
 
 int launch_sample_collide(const double* coef, const double* dur, int B, int n, int K, int S,
                           const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
                           cudaStream_t stream) {
   if (B == 0) return MST_OK;
-  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * FUSED_WARPS * FUSED_WT * (size_t)(n + 2);
-  if (smem > MST_MAX_SMEM - 2048) return MST_ERR_TOO_LARGE;
+  const size_t smem = robot->layout.bytes + env->layout.bytes +
+                      sizeof(double) * ((size_t)env->T * robot->V + FUSED_WARPS * FUSED_WT * (size_t)(n + 2));
+  if (smem > MST_MAX_SMEM - 10240) return MST_ERR_TOO_LARGE;
   auto kern = K == 3 ? sample_collide_kernel<3> : sample_collide_kernel<4>;
   if (smem > 40 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MST_MAX_SMEM);
