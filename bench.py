@@ -293,32 +293,23 @@ def run_ours(args):
     bad = int((res.info != 0).sum().item())
     hit_rate = float(res.any_hit.float().mean().item())
 
-    # --- dominant kernel alone, timed live with CUDA events on the launching stream ------
+    # --- the two kernels of the step alone, timed live with CUDA events on the launching stream
     stage_ms = {}
-    coef_d, dur_d, info_d = res.coef, res.dur, res.info
     ws = torch.empty((max(1, lib.mst_solve_workspace_bytes(B, N_SEG, K_AX, 1)),), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
     def solve_only():
         _abi.check(lib.mst_solve_batch(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO,
-                                       coef_d.data_ptr(), dur_d.data_ptr(), info_d.data_ptr(), ws.data_ptr(),
+                                       res.coef.data_ptr(), res.dur.data_ptr(), res.info.data_ptr(), ws.data_ptr(),
                                        st), "mst_solve_batch")
-    solve_only()
-    stage_ms["solve"] = timed(solve_only, args.steps) / args.steps
-    nb = min(B, 1 << 16)
-    pos = torch.empty((nb, S_SAMPLES, K_AX), dtype=torch.float64, device=dev)
-    hitb = torch.empty((nb * S_SAMPLES,), dtype=torch.uint8, device=dev)
-
-    def sample_only():
-        _abi.check(lib.mst_sample_batch(coef_d.data_ptr(), dur_d.data_ptr(), nb, N_SEG, K_AX, None, 0, S_SAMPLES,
-                                        0, 0, pos.data_ptr(), None, st), "mst_sample_batch")
 
     def collide_only():
-        _abi.check(lib.mst_collide_poses(robot.handle, env.handle, pos.data_ptr(), nb * S_SAMPLES, K_AX,
-                                         hitb.data_ptr(), st), "mst_collide_poses")
-    sample_only(); collide_only()
-    stage_ms["sample"] = timed(sample_only, args.steps) / args.steps * (B / nb)
-    stage_ms["collide"] = timed(collide_only, args.steps) / args.steps * (B / nb)
+        _abi.check(lib.mst_collide_trajectories(res.coef.data_ptr(), res.dur.data_ptr(), B, N_SEG, K_AX, S_SAMPLES,
+                                                robot.handle, env.handle, res.hit.data_ptr(), res.any_hit.data_ptr(),
+                                                st), "mst_collide_trajectories")
+    solve_only(); collide_only()
+    stage_ms["condensed_kernel (+ banded_lu_kernel on the declined list)"] = timed(solve_only, args.steps) / args.steps
+    stage_ms["sample_collide_kernel"] = timed(collide_only, args.steps) / args.steps
 
     peaks = {}
     try:
@@ -328,9 +319,14 @@ def run_ours(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    dominant = max(stage_ms, key=stage_ms.get)
-    # the pipeline's compulsory traffic charged to the whole step: the stages are one logical kernel
-    achieved = B * ALG_BYTES / (ms_per_step * 1e-3) / 1e9 if world == 1 else None
+    # dominant kernel: sample_collide_kernel.  Its compulsory bytes per trajectory: coefficients
+    # and durations in, per-sample flags + any-flag out.
+    dom_ms = stage_ms["sample_collide_kernel"]
+    dom_bytes = N_SEG * K_AX * 64 + N_SEG * 8 + S_SAMPLES + 1
+    achieved = B * dom_bytes / (dom_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/ (ncu --set full,
+    # 262,144 trajectories per launch, cold L2), scaled to this launch's trajectory count
+    traffic_per_traj = (525.209344e6 + 26.705920e6) / 262144
 
     # --- end to end through HOST buffers (pinned), copies inside the timed region ----------
     hp = HostPipeline(N_SEG, K_AX, S_SAMPLES, robot, env, chunk=args.e2e_chunk)
@@ -362,10 +358,14 @@ def run_ours(args):
                 "chunk": hp.chunk, "note": "pinned host in/out, 3-slot copy/compute overlap"},
         "gpu_launches": args.steps * n_chunks * lib.mst_pipeline_launch_count(B // n_chunks, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
-                     "peak_source": peak_src, "alg_bytes_per_trajectory": ALG_BYTES,
-                     "kernel": "whole pipeline step (dominant stage: %s)" % dominant,
-                     "stage_ms": stage_ms},
+                     "frac": achieved / peak_gbs, "traffic": traffic_per_traj * B,
+                     "peak_source": peak_src, "kernel": "sample_collide_kernel<3> (%.0f %% of the step)"
+                     % (100 * dom_ms / ms_per_step if world == 1 else 100 * dom_ms / sum(stage_ms.values())),
+                     "alg_bytes_per_trajectory": dom_bytes, "trajectories_per_launch": B,
+                     "kernel_ms": dom_ms, "kernels_ms": stage_ms,
+                     "whole_step": {"alg_bytes_per_trajectory": ALG_BYTES,
+                                    "achieved_gbs": (B * ALG_BYTES / (ms_per_step * 1e-3) / 1e9) if world == 1 else None},
+                     "note": "instruction/latency bound (branchy FP64 geometry), not bandwidth bound: see profiles/"},
         "checks": {"solver_failures": bad, "any_hit_rate": hit_rate},
     }
 

@@ -254,6 +254,22 @@ def collide_poses(robot: Mesh, env: Mesh, poses) -> torch.Tensor:
     return hit
 
 
+def collide_trajectories(coef, dur, S: int, robot: Mesh, env: Mesh):
+    """Sample ``S`` uniform times of every trajectory and collision-check the robot mesh placed
+    there; returns ``hit[B, S]``, ``any_hit[B]`` (the pipeline's second kernel on its own)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    coef = _f64(coef, dev)
+    dur = _f64(dur, dev)
+    B, n, K, _ = coef.shape
+    hit = torch.empty((B, S), dtype=torch.uint8, device=dev)
+    any_hit = torch.empty((B,), dtype=torch.uint8, device=dev)
+    rc = lib.mst_collide_trajectories(_ptr(coef), _ptr(dur), B, n, K, S, robot.handle, env.handle, _ptr(hit),
+                                      _ptr(any_hit), _stream_ptr())
+    _abi.check(rc, "mst_collide_trajectories")
+    return hit, any_hit
+
+
 # --------------------------------------------------------------------------- fused pipeline
 class PipelineResult:
     __slots__ = ("coef", "dur", "info", "hit", "any_hit")

@@ -179,6 +179,15 @@ extern "C" int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double*
   return launch_collide(robot, env, pose, P, pose_dim, hit, (cudaStream_t)stream);
 }
 
+extern "C" int mst_collide_trajectories(const double* coef, const double* dur, int B, int n, int K, int S,
+                                        mst_mesh_t robot, mst_mesh_t env, uint8_t* hit, uint8_t* any_hit,
+                                        void* stream) {
+  if (S < 1 || (K != 3 && K != 4) || !robot || !env || B < 0 || n < 1) return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!coef || !dur || !hit || !any_hit) return MST_ERR_INVALID;
+  return launch_sample_collide(coef, dur, B, n, K, S, robot, env, hit, any_hit, (cudaStream_t)stream);
+}
+
 extern "C" size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_time_group, int S) {
   (void)S;
   if (B < 0 || K < 1 || n < 1 || share_time_group < 1) return 0;

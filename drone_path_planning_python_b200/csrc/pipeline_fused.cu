@@ -121,10 +121,12 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       const double* kn = knots + tl * (n + 1);
       const double t = __dmul_rn((double)s, dts[tl]);
       // PiecewisePolynomial.eval: first piece with t < acc + T_i, else the last one at
-      // t - sum(T[:-1])
-      int piece = n - 1;
-      for (int i = 0; i < n; ++i)
-        if (t < kn[i + 1]) { piece = i; break; }
+      // t - sum(T[:-1]); the running sums are non-decreasing, so bisection finds the same piece
+      int piece = 0, last = n - 1;
+      while (piece < last) {
+        const int mid = (piece + last) >> 1;
+        if (t < kn[mid + 1]) last = mid; else piece = mid + 1;
+      }
       const double local = __dsub_rn(t, kn[piece]);
       const double* cp = coef + (((size_t)(b0 + tl) * n + piece) * K) * MST_NCOEF;
       double pos[K];

@@ -186,6 +186,16 @@ int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double* pose, int 
                       int pose_dim, uint8_t* hit, void* stream);
 
 /*
+ * Collision-check already solved trajectories (the second kernel of the pipeline on its own):
+ * sample S uniform times per trajectory, robot mesh at each sampled position (yaw = 4th axis
+ * when K = 4, else 0), flags as in mst_pipeline.  K must be 3 or 4.
+ *   coef [B][n][K][8], dur [B][n]  ->  hit [B][S], any_hit [B]
+ */
+int mst_collide_trajectories(const double* coef, const double* dur, int B, int n, int K, int S,
+                             mst_mesh_t robot, mst_mesh_t env, uint8_t* hit, uint8_t* any_hit,
+                             void* stream);
+
+/*
  * Fused pipeline: solve -> sample S uniform times -> place the robot mesh at every
  * sampled position (yaw = sampled 4th axis when K = 4, else 0) -> collide.
  *   inputs / coef / dur / info as mst_solve_batch
