@@ -19,6 +19,17 @@ int check_launch() {
   return MST_OK;
 }
 
+int allow_dynamic_smem(const void* kernel, size_t dynamic_bytes) {
+  cudaFuncAttributes attr;
+  cudaError_t e = cudaFuncGetAttributes(&attr, kernel);
+  if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  if (attr.sharedSizeBytes + dynamic_bytes > MST_MAX_SMEM) return MST_ERR_TOO_LARGE;
+  if (dynamic_bytes <= 48 * 1024) return MST_OK;  // within the default limit
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynamic_bytes);
+  if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  return MST_OK;
+}
+
 // kernels' host launchers (one per .cu file)
 size_t banded_lu_smem_per_warp(int n, int R);
 int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K, int G, const int* list,

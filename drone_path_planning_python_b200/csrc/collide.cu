@@ -93,11 +93,9 @@ int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pos
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;
   const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * (size_t)env->T * robot->V;
-  if (smem > MST_MAX_SMEM - 10240) return MST_ERR_TOO_LARGE;
-  if (smem > 40 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         MST_MAX_SMEM);
-    if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  {
+    const int rc = allow_dynamic_smem((const void*)collide_kernel, smem);
+    if (rc != MST_OK) return rc;
   }
   long long blocks = (P + 127) / 128;
   const long long cap = (long long)MST_SM_COUNT * 16;

@@ -14,6 +14,9 @@ namespace mst {
 // set by every failed CUDA call; read back through mst_last_cuda_error()
 void note_cuda_error(cudaError_t e);
 int check_launch();
+// opt a kernel in to `dynamic_bytes` of dynamic shared memory (on top of its static usage);
+// MST_ERR_TOO_LARGE when static + dynamic exceed what one CTA can have on sm_100a
+int allow_dynamic_smem(const void* kernel, size_t dynamic_bytes);
 
 // k!/(k-j)! for 0 <= j <= k <= 7 (exact in double)
 __host__ __device__ __forceinline__ double falling_factorial(int k, int j) {

@@ -183,11 +183,10 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
   if (B == 0) return MST_OK;
   const size_t smem = robot->layout.bytes + env->layout.bytes +
                       sizeof(double) * ((size_t)env->T * robot->V + FUSED_WARPS * FUSED_WT * (size_t)(n + 2));
-  if (smem > MST_MAX_SMEM - 10240) return MST_ERR_TOO_LARGE;
   auto kern = K == 3 ? sample_collide_kernel<3> : sample_collide_kernel<4>;
-  if (smem > 40 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MST_MAX_SMEM);
-    if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  {
+    const int rc = allow_dynamic_smem((const void*)kern, smem);
+    if (rc != MST_OK) return rc;
   }
   const int tiles = (B + FUSED_WT - 1) / FUSED_WT;
   int blocks = (tiles + FUSED_WARPS - 1) / FUSED_WARPS;

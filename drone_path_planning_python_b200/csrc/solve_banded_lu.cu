@@ -198,10 +198,9 @@ int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K
   if (warps < 1) return MST_ERR_TOO_LARGE;
   if (warps > 16) warps = 16;
   const size_t smem = per_warp * warps;
-  {  // per device and cheap, so set on every launch
-    const cudaError_t e = cudaFuncSetAttribute(banded_lu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               MST_MAX_SMEM);
-    if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  {
+    const int rc = allow_dynamic_smem((const void*)banded_lu_kernel, smem);
+    if (rc != MST_OK) return rc;
   }
   long long blocks = ((long long)groups + warps - 1) / warps;
   const long long cap = (long long)MST_SM_COUNT * 4;
