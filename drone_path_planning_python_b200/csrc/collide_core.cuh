@@ -307,14 +307,11 @@ __device__ __forceinline__ void narrow_phase_items(int count, unsigned head, con
       pose_rotation<POSE>(q, R);
       P1 = xform(R, q, pr); P2 = xform(R, q, pr + 3); P3 = xform(R, q, pr + 6);
     }
-    const double* bx = ev.box + 6 * e;
-    if (!(fmax(fmax(P1.x, P2.x), P3.x) < bx[0] || fmin(fmin(P1.x, P2.x), P3.x) > bx[3] ||
-          fmax(fmax(P1.y, P2.y), P3.y) < bx[1] || fmin(fmin(P1.y, P2.y), P3.y) > bx[4] ||
-          fmax(fmax(P1.z, P2.z), P3.z) < bx[2] || fmin(fmin(P1.z, P2.z), P3.z) > bx[5])) {
-      const double* qe = ev.tri + 9 * e;
-      const V3 Q1 = {qe[0], qe[1], qe[2]}, Q2 = {qe[3], qe[4], qe[5]}, Q3 = {qe[6], qe[7], qe[8]};
-      if (triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3)) atomicOr(&wq[COLLIDE_RING], 1u << src);
-    }
+    // (no triangle-box cull here: the two plane tests that open the interval test reject the
+    // same pairs for fewer instructions — measured, profiles/r1_collision_history.md)
+    const double* qe = ev.tri + 9 * e;
+    const V3 Q1 = {qe[0], qe[1], qe[2]}, Q2 = {qe[3], qe[4], qe[5]}, Q3 = {qe[6], qe[7], qe[8]};
+    if (triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3)) atomicOr(&wq[COLLIDE_RING], 1u << src);
   }
   __syncwarp();
 }
