@@ -22,58 +22,51 @@
 
 namespace mst {
 
-// pose_dim 3: (x,y,z) with identity rotation; 4: (x,y,z,yaw); 7: (x,y,z,qx,qy,qz,qw)
-__global__ void __launch_bounds__(128)
+// POSE 0: pose = (x,y,z), identity rotation; 1: (x,y,z,yaw); 2: (x,y,z,qx,qy,qz,qw)
+template <int POSE>
+__global__ void __launch_bounds__(128, 4)
 collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
                const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
-               const double* __restrict__ pose, long long P, int pose_dim, uint8_t* __restrict__ hit) {
+               const double* __restrict__ pose, long long P, uint8_t* __restrict__ hit) {
+  constexpr int NP = PoseDim<POSE>::N;
+  constexpr int pose_dim = POSE == 0 ? 3 : (POSE == 1 ? 4 : 7);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ unsigned work_queue[4][COLLIDE_WQ_WORDS];  // per warp: item ring + hit mask
-  unsigned* wq = work_queue[threadIdx.x >> 5];
+  __shared__ PoseRing<NP> rings[4];
+  PoseRing<NP>& ring = rings[threadIdx.x >> 5];
   stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
   const MeshView rb = mesh_view(smem_raw, rl);
   const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
-  const bool culled = rb.V <= COLLIDE_MAX_V && rb.T < 4096 && ev.T < 4096;
+  const bool engine = collide_engine_supports(rb, ev);
   double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);  // plane x vertex table
-  if (culled && pose_dim == 3) build_plane_vertex_table(rb, ev, nv);
+  if (engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
   __syncthreads();
-  // warp-uniform trip count (the collision test votes across the warp)
+  unsigned ring_head = 0u, ring_tail = 0u;  // warp-uniform
+  auto report = [&](int hi32, int lo32, bool h) {
+    hit[((long long)hi32 << 32) | (unsigned)lo32] = h ? 1 : 0;
+  };
+  // warp-uniform trip count (the ring operations vote across the warp)
   for (long long base = blockIdx.x * (long long)blockDim.x; base < P; base += (long long)gridDim.x * blockDim.x) {
     const long long idx = base + threadIdx.x;
     const bool active = idx < P;
     const double* ps = pose + (active ? idx : P - 1) * pose_dim;
-    bool h;
-    if (pose_dim == 3) {
-      const double pp[3] = {ps[0], ps[1], ps[2]};
-      if (culled) {
-        h = robot_hits_env_queue<0>(active, pp, rb, rbb, ev, evb, nv, wq);
-      } else {
-        const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
-      }
-    } else if (pose_dim == 4) {
-      double pp[5] = {ps[0], ps[1], ps[2], 0.0, 0.0};
-      sincos(ps[3] * 0.5, &pp[3], &pp[4]);
-      if (culled) {
-        h = robot_hits_env_queue<1>(active, pp, rb, rbb, ev, evb, nv, wq);
-      } else {
-        double R[9];
-        quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
-        h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
-      }
-    } else {
-      const double pp[7] = {ps[0], ps[1], ps[2], ps[3], ps[4], ps[5], ps[6]};
-      if (culled) {
-        h = robot_hits_env_queue<2>(active, pp, rb, rbb, ev, evb, nv, wq);
-      } else {
-        double R[9];
-        quat_to_matrix(pp[3], pp[4], pp[5], pp[6], R);
-        h = active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, false);
-      }
+    double pp[NP];
+    pp[0] = ps[0]; pp[1] = ps[1]; pp[2] = ps[2];
+    if (POSE == 1) sincos(ps[3] * 0.5, &pp[3], &pp[4]);
+    if (POSE == 2) { pp[3] = ps[3]; pp[4] = ps[4]; pp[5] = ps[5]; pp[6] = ps[6]; }
+    if (!engine) {  // meshes the bit-mask cursors cannot hold: plain per-lane test over all pairs
+      double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      pose_rotation<POSE>(pp, R);
+      if (active) hit[idx] = robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, POSE != 2) ? 1 : 0;
+      continue;
     }
-    if (active) hit[idx] = h ? 1 : 0;
+    const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
+    if (active && !near) hit[idx] = 0;
+    ring_push<POSE>(ring, ring_tail, near, pp, (int)(idx >> 32), (int)(idx & 0xffffffffll), -1, 0u);
+    while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
   }
+  while (ring_tail != ring_head)
+    ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
 // any_hit[b] = OR_s hit[b][s]; one warp per trajectory
@@ -93,16 +86,17 @@ int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pos
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;
   const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * (size_t)env->T * robot->V;
+  void (*kern)(const void*, MeshLayout, MeshBounds, const void*, MeshLayout, MeshBounds, const double*, long long,
+               uint8_t*) = pose_dim == 3 ? collide_kernel<0> : (pose_dim == 4 ? collide_kernel<1> : collide_kernel<2>);
   {
-    const int rc = allow_dynamic_smem((const void*)collide_kernel, smem);
+    const int rc = allow_dynamic_smem((const void*)kern, smem);
     if (rc != MST_OK) return rc;
   }
   long long blocks = (P + 127) / 128;
-  const long long cap = (long long)MST_SM_COUNT * 16;
+  const long long cap = (long long)MST_SM_COUNT * 4;
   if (blocks > cap) blocks = cap;
-  collide_kernel<<<(unsigned)blocks, 128, smem, stream>>>(robot->d_image, robot->layout, robot->bounds,
-                                                          env->d_image, env->layout, env->bounds, pose, P,
-                                                          pose_dim, hit);
+  kern<<<(unsigned)blocks, 128, smem, stream>>>(robot->d_image, robot->layout, robot->bounds, env->d_image,
+                                                env->layout, env->bounds, pose, P, hit);
   return check_launch();
 }
 
@@ -151,3 +145,4 @@ extern "C" int mst_mesh_destroy(mst_mesh_t mesh) {
 }
 
 extern "C" int mst_mesh_triangle_count(mst_mesh_t mesh) { return mesh ? mesh->T : MST_ERR_INVALID; }
+

@@ -241,29 +241,37 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------
-// Warp-cooperative form of robot_hits_env_culled with WORK COMPACTION: lane <-> pose for the
-// broad phase, lane <-> (pose, robot triangle, env triangle) item for the narrow phase.
+// Warp-level collision engine used by the kernels: a ring of poses waiting for the test,
+// drained 32 at a time, every lane walking ITS pose's candidate triangle pairs lazily and
+// stopping at the first hit.
 //
-// A profile of the per-lane version (profiles/r1_collision_history.md) showed ~86 % of all
-// issued instructions inside the SAT with 4.5 of 32 lanes active: neighbouring poses survive
-// the culls with DIFFERENT triangle pairs, so the lanes serialise.  Here the broad phase
-// (bounding boxes, the env plane against all robot vertices, the vertex masks — the very same
-// predicates) only ENQUEUES surviving (lane, e, r) triples into a ring in shared memory:
-// every lane collects the robot triangles it needs against env triangle e as a bit mask, one
-// warp prefix sum hands out the slots, and whenever 32 items are waiting the warp runs the
-// pair test on 32 different items at once (the pose of the item's source lane comes by
-// shuffle); a hit is OR-ed into a per-warp bit mask.  The pair test is the interval form
-// (triangles_intersect_interval), equal to the 17-axis SAT away from touching.
+// How it got here (profiles/r1_collision_history.md): a per-lane loop over all pairs ran the
+// pair test with 4.5/32 lanes active (neighbouring poses survive the culls with different
+// pairs); compacting (pose, e, r) items across the warp fixed the lane utilisation but still
+// tested every candidate pair of every pose — and on the benchmark's trajectories 99 % of the
+// poses whose box reaches the obstacle's box do collide, with the first intersecting pair
+// among the first 2 candidates for two thirds of them (23 candidates on average).  So the
+// work to avoid is everything after the first hit:
+//   * a pose enters the ring only if it passes the root-box culls (pose_near_environment);
+//   * draining 32 poses, each lane advances a CURSOR (env triangle e, bit mask of the robot
+//     triangles still to test against e) to its next candidate — the culls are the same
+//     exact-safe ones: env-triangle box, env plane against all unique robot vertices
+//     ("above"/"below" bit masks), robot triangles whose corner bits agree are skipped — and
+//     all lanes that have a candidate run the pair test together (interval form);
+//   * after ROUNDS candidates a pose that is still undecided goes back to the tail of the
+//     ring WITH its cursor, so the next batch is dense again instead of 32 lanes waiting for
+//     the slowest one.
+// A pose is reported (hit or free) exactly once.  The answer equals the brute-force test over
+// all pairs: stopping early only skips pairs after a hit.
 //
 // POSE: 0 translation (x,y,z); 1 yaw (x,y,z,sin(yaw/2),cos(yaw/2)); 2 quaternion
-// (x,y,z,qx,qy,qz,qw).  wq: COLLIDE_WQ_WORDS unsigned of shared memory owned by this warp.
-// nv (POSE 0 only): table nv[e][v] = n_e . v of plane normals against the robot's unique
-// vertices (build_plane_vertex_table) — a translation leaves it constant, so the signed
+// (x,y,z,qx,qy,qz,qw).  nv (POSE 0 only): table nv[e][v] = n_e . v of env plane normals
+// against the robot's unique vertices — a translation leaves it constant, so the signed
 // distance of vertex v to plane e is one add.
-constexpr int COLLIDE_RING = 512;                     // entries; a power of two
-constexpr int COLLIDE_RBLOCK = 15;                    // robot triangles enqueued per round: 31 + 32*15 <= 512
-constexpr int COLLIDE_WQ_WORDS = COLLIDE_RING + 1;    // + the per-warp hit mask
-constexpr int COLLIDE_MAX_V = 32;                     // unique robot vertices the bit masks can hold
+constexpr int COLLIDE_MAX_V = 32;    // unique robot vertices the bit masks can hold
+constexpr int COLLIDE_MAX_TR = 32;   // robot triangles the cursor's bit mask can hold
+constexpr int COLLIDE_RING = 64;     // poses per warp ring (a power of two, >= 2 * 32)
+constexpr int COLLIDE_ROUNDS = 2;    // candidates tested per pose and drain
 
 template <int POSE> struct PoseDim { static constexpr int N = POSE == 0 ? 3 : (POSE == 1 ? 5 : 7); };
 
@@ -271,6 +279,10 @@ template <int POSE>
 __device__ __forceinline__ void pose_rotation(const double* pp, double* R) {
   if (POSE == 1) quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
   if (POSE == 2) quat_to_matrix(pp[3], pp[4], pp[5], pp[6], R);
+}
+
+__host__ __device__ __forceinline__ bool collide_engine_supports(const MeshView& rb, const MeshView& ev) {
+  return rb.V <= COLLIDE_MAX_V && rb.T <= COLLIDE_MAX_TR && ev.T < (1 << 20);
 }
 
 // nv[e * V + v] = n_e . vertex_v ; every thread of the CTA calls it, followed by a CTA barrier
@@ -283,184 +295,175 @@ __device__ __forceinline__ void build_plane_vertex_table(const MeshView& rb, con
   }
 }
 
+// world box of the robot at a pose: exact for a translation, else the box of the rotated local box
 template <int POSE>
-__device__ __forceinline__ void narrow_phase_items(int count, unsigned head, const double* pp, const MeshView& rb,
-                                                   const MeshView& ev, unsigned* wq) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const bool valid = lane < count;
-  const unsigned item = valid ? wq[(head + lane) & (COLLIDE_RING - 1)] : 0u;
-  const int src = valid ? (int)(item >> 24) : lane;
-  const int e = (int)((item >> 12) & 0xfffu), r = (int)(item & 0xfffu);
-  double q[PoseDim<POSE>::N];
-#pragma unroll
-  for (int i = 0; i < PoseDim<POSE>::N; ++i) q[i] = __shfl_sync(FULL, pp[i], src);
-  if (valid && !((wq[COLLIDE_RING] >> src) & 1u)) {
-    const double* pr = rb.tri + 9 * r;
-    V3 P1, P2, P3;
-    if (POSE == 0) {
-      P1 = {pr[0] + q[0], pr[1] + q[1], pr[2] + q[2]};
-      P2 = {pr[3] + q[0], pr[4] + q[1], pr[5] + q[2]};
-      P3 = {pr[6] + q[0], pr[7] + q[1], pr[8] + q[2]};
-    } else {
-      double R[9];
-      pose_rotation<POSE>(q, R);
-      P1 = xform(R, q, pr); P2 = xform(R, q, pr + 3); P3 = xform(R, q, pr + 6);
+__device__ __forceinline__ void robot_world_box(const double* pp, const double* R, const MeshBounds& rbb,
+                                                double* lo, double* hi) {
+  const double* T = pp;
+  if (POSE == 0) {
+    lo[0] = rbb.root[0] + T[0]; lo[1] = rbb.root[1] + T[1]; lo[2] = rbb.root[2] + T[2];
+    hi[0] = rbb.root[3] + T[0]; hi[1] = rbb.root[4] + T[1]; hi[2] = rbb.root[5] + T[2];
+  } else {
+    const double c0 = 0.5 * (rbb.root[0] + rbb.root[3]), c1 = 0.5 * (rbb.root[1] + rbb.root[4]),
+                 c2 = 0.5 * (rbb.root[2] + rbb.root[5]);
+    // half extents, padded so rounding in the products below cannot shrink the box
+    const double h0 = 0.5 * (rbb.root[3] - rbb.root[0]), h1 = 0.5 * (rbb.root[4] - rbb.root[1]),
+                 h2 = 0.5 * (rbb.root[5] - rbb.root[2]);
+    const double pad = 1e-12 * (rbb.radius + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
+    for (int a = 0; a < 3; ++a) {
+      const double w = R[3 * a] * c0 + R[3 * a + 1] * c1 + R[3 * a + 2] * c2 + T[a];
+      const double ext = fabs(R[3 * a]) * h0 + fabs(R[3 * a + 1]) * h1 + fabs(R[3 * a + 2]) * h2 + pad;
+      lo[a] = w - ext;
+      hi[a] = w + ext;
     }
-    // (no triangle-box cull here: the two plane tests that open the interval test reject the
-    // same pairs for fewer instructions — measured, profiles/r1_collision_history.md)
-    const double* qe = ev.tri + 9 * e;
-    const V3 Q1 = {qe[0], qe[1], qe[2]}, Q2 = {qe[3], qe[4], qe[5]}, Q3 = {qe[6], qe[7], qe[8]};
-    if (triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3)) atomicOr(&wq[COLLIDE_RING], 1u << src);
   }
-  __syncwarp();
 }
 
 // lane-local: can the robot at this pose touch the environment's root box at all?
-// (bounding sphere for rigid poses, then the robot's world box) — the first two culls of
-// robot_hits_env_queue, exposed so callers can compact the surviving poses first
+// (bounding sphere for rigid poses, then the robot's world box)
 template <int POSE>
 __device__ __forceinline__ bool pose_near_environment(const double* pp, const MeshBounds& rbb, const MeshBounds& evb) {
   const double* root = evb.root;
   const double* T = pp;
-  if (POSE != 2 && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
-                    T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
-    return false;
-  double lo0, lo1, lo2, hi0, hi1, hi2;
-  if (POSE == 0) {
-    lo0 = rbb.root[0] + T[0]; lo1 = rbb.root[1] + T[1]; lo2 = rbb.root[2] + T[2];
-    hi0 = rbb.root[3] + T[0]; hi1 = rbb.root[4] + T[1]; hi2 = rbb.root[5] + T[2];
-  } else {
-    double R[9];
-    pose_rotation<POSE>(pp, R);
-    const double c0 = 0.5 * (rbb.root[0] + rbb.root[3]), c1 = 0.5 * (rbb.root[1] + rbb.root[4]),
-                 c2 = 0.5 * (rbb.root[2] + rbb.root[5]);
-    const double h0 = 0.5 * (rbb.root[3] - rbb.root[0]), h1 = 0.5 * (rbb.root[4] - rbb.root[1]),
-                 h2 = 0.5 * (rbb.root[5] - rbb.root[2]);
-    const double pad = 1e-12 * (rbb.radius + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
-    const double w0 = R[0] * c0 + R[1] * c1 + R[2] * c2 + T[0], w1 = R[3] * c0 + R[4] * c1 + R[5] * c2 + T[1],
-                 w2 = R[6] * c0 + R[7] * c1 + R[8] * c2 + T[2];
-    const double e0 = fabs(R[0]) * h0 + fabs(R[1]) * h1 + fabs(R[2]) * h2 + pad,
-                 e1 = fabs(R[3]) * h0 + fabs(R[4]) * h1 + fabs(R[5]) * h2 + pad,
-                 e2 = fabs(R[6]) * h0 + fabs(R[7]) * h1 + fabs(R[8]) * h2 + pad;
-    lo0 = w0 - e0; hi0 = w0 + e0; lo1 = w1 - e1; hi1 = w1 + e1; lo2 = w2 - e2; hi2 = w2 + e2;
-  }
-  return !(hi0 < root[0] || lo0 > root[3] || hi1 < root[1] || lo1 > root[4] || hi2 < root[2] || lo2 > root[5]);
-}
-
-template <int POSE>
-__device__ __forceinline__ bool robot_hits_env_queue(bool active, const double* pp, const MeshView& rb,
-                                                     const MeshBounds& rbb, const MeshView& ev,
-                                                     const MeshBounds& evb, const double* nv, unsigned* wq) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const double* root = evb.root;
-  const double* T = pp;
-  bool near = active;
   // POSE 2 takes whatever quaternion the caller gave (maybe not unit): no sphere cull there
   if (POSE != 2 && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
                     T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
-    near = false;
-  if (!__any_sync(FULL, near)) return false;
-  double R[9];
+    return false;
+  double R[9], lo[3], hi[3];
   pose_rotation<POSE>(pp, R);
-  double lo0, lo1, lo2, hi0, hi1, hi2;
-  if (POSE == 0) {
-    lo0 = rbb.root[0] + T[0]; lo1 = rbb.root[1] + T[1]; lo2 = rbb.root[2] + T[2];
-    hi0 = rbb.root[3] + T[0]; hi1 = rbb.root[4] + T[1]; hi2 = rbb.root[5] + T[2];
-  } else {
-    const double c0 = 0.5 * (rbb.root[0] + rbb.root[3]), c1 = 0.5 * (rbb.root[1] + rbb.root[4]),
-                 c2 = 0.5 * (rbb.root[2] + rbb.root[5]);
-    const double h0 = 0.5 * (rbb.root[3] - rbb.root[0]), h1 = 0.5 * (rbb.root[4] - rbb.root[1]),
-                 h2 = 0.5 * (rbb.root[5] - rbb.root[2]);
-    const double pad = 1e-12 * (rbb.radius + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
-    const double w0 = R[0] * c0 + R[1] * c1 + R[2] * c2 + T[0], w1 = R[3] * c0 + R[4] * c1 + R[5] * c2 + T[1],
-                 w2 = R[6] * c0 + R[7] * c1 + R[8] * c2 + T[2];
-    const double e0 = fabs(R[0]) * h0 + fabs(R[1]) * h1 + fabs(R[2]) * h2 + pad,
-                 e1 = fabs(R[3]) * h0 + fabs(R[4]) * h1 + fabs(R[5]) * h2 + pad,
-                 e2 = fabs(R[6]) * h0 + fabs(R[7]) * h1 + fabs(R[8]) * h2 + pad;
-    lo0 = w0 - e0; hi0 = w0 + e0; lo1 = w1 - e1; hi1 = w1 + e1; lo2 = w2 - e2; hi2 = w2 + e2;
-  }
-  if (hi0 < root[0] || lo0 > root[3] || hi1 < root[1] || lo1 > root[4] || hi2 < root[2] || lo2 > root[5])
-    near = false;
-  if (!__any_sync(FULL, near)) return false;
-  if (lane == 0) wq[COLLIDE_RING] = 0u;
+  robot_world_box<POSE>(pp, R, rbb, lo, hi);
+  return !(hi[0] < root[0] || lo[0] > root[3] || hi[1] < root[1] || lo[1] > root[4] || hi[2] < root[2] ||
+           lo[2] > root[5]);
+}
+
+// per-warp ring of poses waiting for (more of) the collision test
+
+template <int NP>
+struct PoseRing {
+  double pose[COLLIDE_RING][NP];
+  int id0[COLLIDE_RING], id1[COLLIDE_RING];  // caller's identification of the pose
+  int e[COLLIDE_RING];                       // cursor: env triangle whose `need` bits are current (-1: none yet)
+  unsigned need[COLLIDE_RING];               // cursor: robot triangles still to test against triangle e
+};
+
+// append the poses of the lanes with `push` set (ballot-compacted); all 32 lanes call it
+template <int POSE>
+__device__ __forceinline__ void ring_push(PoseRing<PoseDim<POSE>::N>& ring, unsigned& tail, bool push, const double* pp,
+                                          int id0, int id1, int e, unsigned need) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   __syncwarp();
-  unsigned head = 0u, tail = 0u;  // ring positions (warp-uniform)
-  const unsigned all = rb.V >= 32 ? ~0u : ((1u << rb.V) - 1u);
-  for (int e = 0; e < ev.T; ++e) {
-    const double* bx = ev.box + 6 * e;
-    bool pass = near && !(hi0 < bx[0] || lo0 > bx[3] || hi1 < bx[1] || lo1 > bx[4] || hi2 < bx[2] || lo2 > bx[5]);
-    if (!__any_sync(FULL, pass)) continue;
-    unsigned above = 0u, below = 0u;
-    if (pass) {
-      const double* pl = ev.plane + 4 * e;
-      const double off = pl[0] * T[0] + pl[1] * T[1] + pl[2] * T[2] - pl[3];
-      if (POSE == 0) {
-        const double* row = nv + e * rb.V;
-        for (int v = 0; v < rb.V; ++v) {
-          const double dist = row[v] + off;
-          above |= (unsigned)(dist > 0.0) << v;
-          below |= (unsigned)(dist < 0.0) << v;
-        }
-      } else {
-        // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
-        const double m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
-        const double m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
-        const double m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
-        for (int v = 0; v < rb.V; ++v) {
-          const double* p = rb.vert + 3 * v;
-          const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
-          above |= (unsigned)(dist > 0.0) << v;
-          below |= (unsigned)(dist < 0.0) << v;
-        }
-      }
-      if (above == all || below == all) pass = false;
-    }
-    if (!__any_sync(FULL, pass)) continue;
-    for (int r0 = 0; r0 < rb.T; r0 += COLLIDE_RBLOCK) {
-      const int rn = min(COLLIDE_RBLOCK, rb.T - r0);
-      unsigned need = 0u;  // bit j: robot triangle r0+j has corners on both sides of (or on) plane e
-      if (pass) {
-        for (int j = 0; j < rn; ++j) {
-          const unsigned mk = (unsigned)rb.mask[r0 + j];
-          need |= (unsigned)(!((above & mk) == mk || (below & mk) == mk)) << j;
-        }
-      }
-      // slots: exclusive prefix sum of the per-lane counts
-      const int cnt = __popc(need);
-      int inc = cnt;
+  const unsigned vote = __ballot_sync(FULL, push);
+  if (!vote) return;
+  if (push) {
+    const unsigned slot = (tail + __popc(vote & ((1u << lane) - 1u))) & (COLLIDE_RING - 1);
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int up = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += up;
+    for (int i = 0; i < PoseDim<POSE>::N; ++i) ring.pose[slot][i] = pp[i];
+    ring.id0[slot] = id0; ring.id1[slot] = id1; ring.e[slot] = e; ring.need[slot] = need;
+  }
+  tail += __popc(vote);
+  __syncwarp();
+}
+
+// test up to COLLIDE_ROUNDS candidates for each of the first `count` waiting poses; decided
+// poses are handed to report(id0, id1, hit), the others return to the tail with their cursor
+template <int POSE, class Report>
+__device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, unsigned& head, unsigned& tail, int count,
+                                           const MeshView& rb, const MeshBounds& rbb, const MeshView& ev,
+                                           const double* nv, Report&& report) {
+  constexpr int NP = PoseDim<POSE>::N;
+  const int lane = threadIdx.x & 31;
+  const bool valid = lane < count;
+  const unsigned slot = (head + (valid ? lane : 0)) & (COLLIDE_RING - 1);
+  double pp[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) pp[i] = ring.pose[slot][i];
+  const int id0 = ring.id0[slot], id1 = ring.id1[slot];
+  int e = ring.e[slot];
+  unsigned need = ring.need[slot];
+  __syncwarp();  // entries are in registers: the slots may be reused by the re-queue below
+  head += (unsigned)count;
+
+  double R[9], lo[3], hi[3];
+  pose_rotation<POSE>(pp, R);
+  robot_world_box<POSE>(pp, R, rbb, lo, hi);
+  const unsigned all = rb.V >= 32 ? ~0u : ((1u << rb.V) - 1u);
+  bool hit = false, exhausted = !valid;
+#pragma unroll 1
+  for (int round = 0; round < COLLIDE_ROUNDS; ++round) {
+    bool have = false;
+    int r = 0;
+    if (!hit && !exhausted) {
+      // Advance the cursor to the next candidate pair.  Keep this loop SINGLE-EXIT: a version
+      // with `break` / `continue` compiled (nvcc 12.9, sm_100a) to BSSY.RELIABLE/BREAK control
+      // flow that left the warp split at the ballot of the re-queue below — ptxas emits that
+      // ballot as a bare VOTE and drops explicit warp barriers as redundant — so the fragments
+      // advanced `tail` differently and ring entries were overwritten (poses never reported;
+      // caught by tests/test_gpu_collision.py::test_every_pose_is_answered_once).
+      while (need == 0u && !exhausted) {
+        ++e;
+        if (e >= ev.T) {
+          exhausted = true;
+        } else {
+          const double* bx = ev.box + 6 * e;
+          if (!(hi[0] < bx[0] || lo[0] > bx[3] || hi[1] < bx[1] || lo[1] > bx[4] || hi[2] < bx[2] || lo[2] > bx[5])) {
+            const double* pl = ev.plane + 4 * e;
+            const double off = pl[0] * pp[0] + pl[1] * pp[1] + pl[2] * pp[2] - pl[3];
+            unsigned above = 0u, below = 0u;
+            if (POSE == 0) {
+              const double* row = nv + e * rb.V;
+              for (int v = 0; v < rb.V; ++v) {
+                const double dist = row[v] + off;
+                above |= (unsigned)(dist > 0.0) << v;
+                below |= (unsigned)(dist < 0.0) << v;
+              }
+            } else {
+              // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
+              const double m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
+              const double m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
+              const double m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
+              for (int v = 0; v < rb.V; ++v) {
+                const double* p = rb.vert + 3 * v;
+                const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
+                above |= (unsigned)(dist > 0.0) << v;
+                below |= (unsigned)(dist < 0.0) << v;
+              }
+            }
+            // skip when the whole robot is strictly on one side of the plane
+            if (above != all && below != all) {
+              for (int j = 0; j < rb.T; ++j) {
+                const unsigned mk = (unsigned)rb.mask[j];
+                need |= (unsigned)(!((above & mk) == mk || (below & mk) == mk)) << j;
+              }
+            }
+          }
+        }
       }
-      const int total = __shfl_sync(FULL, inc, 31);
-      if (total == 0) continue;
-      unsigned slot = tail + (unsigned)(inc - cnt);
-      while (need) {
-        const int j = __ffs(need) - 1;
+      if (!exhausted) {
+        r = __ffs(need) - 1;
         need &= need - 1u;
-        wq[slot & (COLLIDE_RING - 1)] = ((unsigned)lane << 24) | ((unsigned)e << 12) | (unsigned)(r0 + j);
-        ++slot;
-      }
-      tail += (unsigned)total;
-      if (tail - head >= 32u) {
-        __syncwarp();
-        do {
-          narrow_phase_items<POSE>(32, head, pp, rb, ev, wq);
-          head += 32u;
-        } while (tail - head >= 32u);
-        // poses already known to collide stop producing work
-        if ((wq[COLLIDE_RING] >> lane) & 1u) near = false;
-        pass = pass && near;
+        have = true;
       }
     }
-    if (!__any_sync(FULL, near)) break;
+    if (have) {
+      const double* pr = rb.tri + 9 * r;
+      V3 P1, P2, P3;
+      if (POSE == 0) {
+        P1 = {pr[0] + pp[0], pr[1] + pp[1], pr[2] + pp[2]};
+        P2 = {pr[3] + pp[0], pr[4] + pp[1], pr[5] + pp[2]};
+        P3 = {pr[6] + pp[0], pr[7] + pp[1], pr[8] + pp[2]};
+      } else {
+        P1 = xform(R, pp, pr); P2 = xform(R, pp, pr + 3); P3 = xform(R, pp, pr + 6);
+      }
+      const double* qe = ev.tri + 9 * e;
+      const V3 Q1 = {qe[0], qe[1], qe[2]}, Q2 = {qe[3], qe[4], qe[5]}, Q3 = {qe[6], qe[7], qe[8]};
+      if (triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3)) hit = true;
+    }
   }
-  __syncwarp();
-  if (tail != head) narrow_phase_items<POSE>((int)(tail - head), head, pp, rb, ev, wq);
-  return active && ((wq[COLLIDE_RING] >> lane) & 1u);
+  // a pose whose last candidate was just consumed and missed may still have later env triangles:
+  // it is "exhausted" only when the cursor ran off the end
+  if (valid && (hit || exhausted)) report(id0, id1, hit);
+  ring_push<POSE>(ring, tail, valid && !hit && !exhausted, pp, id0, id1, e, need);
 }
 #endif  // __CUDACC__
 

@@ -27,15 +27,6 @@ namespace mst {
 constexpr int FUSED_THREADS = 128;
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
 constexpr int FUSED_WT = 4;     // trajectories per warp tile
-constexpr int FUSED_NEAR = 64;  // ring of samples waiting for the collision test, per warp
-
-// per-warp shared memory of the fused kernel
-template <int NP>
-struct NearRing {
-  double pose[FUSED_NEAR][NP];  // x, y, z (, sin(yaw/2), cos(yaw/2))
-  int traj[FUSED_NEAR];
-  int sample[FUSED_NEAR];
-};
 
 // Every WARP walks its own tiles of FUSED_WT trajectories (no CTA-wide barrier after the
 // meshes are staged): a warp that meets the obstacle takes several times longer over a
@@ -44,9 +35,9 @@ struct NearRing {
 //
 // Sampling and collision are decoupled inside the warp: every lane evaluates its sample and
 // applies the root-box cull; samples that fail it get hit = 0 right away, the others are
-// appended (ballot-compacted) to a ring of "near" samples, and only when 32 of them are
-// waiting does the warp run the collision test — on a DENSE batch, whatever mix of near and
-// far samples the trajectories produce.
+// appended (ballot-compacted) to the warp's pose ring, and only when 32 of them are waiting
+// does the warp run the collision engine (collide_core.cuh) — on a DENSE batch, whatever mix
+// of near and far samples the trajectories produce.
 template <int K>
 __global__ void __launch_bounds__(FUSED_THREADS, 4)
 sample_collide_kernel(const double* __restrict__ coef, const double* __restrict__ dur, int B, int n, int S,
@@ -57,41 +48,26 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   constexpr int NP = PoseDim<POSE>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ unsigned work_queue[FUSED_WARPS][COLLIDE_WQ_WORDS];  // per warp: item ring + hit mask
-  __shared__ NearRing<NP> near_ring[FUSED_WARPS];
+  __shared__ PoseRing<NP> rings[FUSED_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned* wq = work_queue[warp];
-  NearRing<NP>& ring = near_ring[warp];
+  PoseRing<NP>& ring = rings[warp];
   stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
   const MeshView rb = mesh_view(smem_raw, rl);
   const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
-  const bool culled = rb.V <= COLLIDE_MAX_V && rb.T < 4096 && ev.T < 4096;
+  const bool engine = collide_engine_supports(rb, ev);
   // behind the meshes: the plane x vertex table, then per-warp tables knots[WT][n+1]
   // (running sums of the durations) and dt[WT]
   double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
-  if (culled && K == 3) build_plane_vertex_table(rb, ev, nv);
+  if (engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
   __syncthreads();
-  double* knots = nv + (culled ? ev.T * rb.V : 0) + warp * FUSED_WT * (n + 2);
+  double* knots = nv + (engine ? ev.T * rb.V : 0) + warp * FUSED_WT * (n + 2);
   double* dts = knots + FUSED_WT * (n + 1);
-  const unsigned FULL = 0xffffffffu;
-  const unsigned lt_mask = (1u << lane) - 1u;
   unsigned ring_head = 0u, ring_tail = 0u;  // warp-uniform
 
-  // collision test of `count` waiting samples (lane <-> ring entry)
-  auto drain = [&](int count) {
-    const bool valid = lane < count;
-    const unsigned slot = (ring_head + (valid ? lane : 0)) & (FUSED_NEAR - 1);
-    double pp[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) pp[i] = ring.pose[slot][i];
-    const int b = ring.traj[slot], s = ring.sample[slot];
-    const bool h = robot_hits_env_queue<POSE>(valid, pp, rb, rbb, ev, evb, nv, wq);
-    if (valid) {
-      hit[(size_t)b * S + s] = h ? 1 : 0;
-      if (h) any_hit[b] = 1;  // zeroed at the start of the trajectory's tile; every writer stores 1
-    }
-    ring_head += (unsigned)count;
-    __syncwarp();
+  // zeroed at the start of the trajectory's tile; every writer of any_hit stores 1
+  auto report = [&](int b, int s, bool h) {
+    hit[(size_t)b * S + s] = h ? 1 : 0;
+    if (h) any_hit[b] = 1;
   };
 
   const int tiles = (B + FUSED_WT - 1) / FUSED_WT;
@@ -147,34 +123,20 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       double pp[NP];
       pp[0] = pos[0]; pp[1] = pos[1]; pp[2] = pos[2];
       if (POSE == 1) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
-      if (!culled) {  // meshes the bit-mask culls cannot hold: plain per-lane test
+      if (!engine) {  // meshes the bit-mask cursors cannot hold: plain per-lane test over all pairs
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         if (POSE == 1) quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
-        if (active) {
-          const bool h = robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true);
-          hit[(size_t)b0 * S + idx] = h ? 1 : 0;
-          if (h) any_hit[b0 + tl] = 1;
-        }
+        if (active) report(b0 + tl, s, robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true));
         continue;
       }
       const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
       if (active && !near) hit[(size_t)b0 * S + idx] = 0;
-      const unsigned vote = __ballot_sync(FULL, near);
-      if (vote) {
-        if (near) {
-          const unsigned slot = (ring_tail + __popc(vote & lt_mask)) & (FUSED_NEAR - 1);
-#pragma unroll
-          for (int i = 0; i < NP; ++i) ring.pose[slot][i] = pp[i];
-          ring.traj[slot] = b0 + tl;
-          ring.sample[slot] = s;
-        }
-        ring_tail += __popc(vote);
-        __syncwarp();
-        if (ring_tail - ring_head >= 32u) drain(32);
-      }
+      ring_push<POSE>(ring, ring_tail, near, pp, b0 + tl, s, -1, 0u);
+      while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
     }
   }
-  if (ring_tail != ring_head) drain((int)(ring_tail - ring_head));
+  while (ring_tail != ring_head)
+    ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
 int launch_sample_collide(const double* coef, const double* dur, int B, int n, int K, int S,

@@ -129,3 +129,53 @@ def test_pipeline_samples_match_oracle_end_to_end():
                                        with_margin=True)
         clear = np.abs(margin) > 1e-7     # positions themselves carry ~1e-12 solver differences
         assert np.array_equal(hit[b][clear], ref[clear]), b
+
+
+@pytest.mark.parametrize("dim", [3, 4, 7])
+def test_every_pose_is_answered_once(dim):
+    """Regression for the warp ring of the collision engine: 1 M poses, output prefilled with a
+    sentinel — every entry must be overwritten with 0/1, identically on a second run and under a
+    permutation of the poses (lost ring entries showed up as never-written flags)."""
+    import torch
+    import drone_path_planning_python_b200 as mst
+    from drone_path_planning_python_b200 import _abi
+    lib = _abi.load()
+    rng = np.random.default_rng(24 + dim)
+    robot_tris, env_tris = _soup("custom_triangle_robot"), _soup("env-scene-ltu-experiment")
+    robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
+    P = 1 << 20
+    poses = torch.as_tensor(_random_poses(rng, P, dim, env_tris), device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(p):
+        out = torch.full((P,), 7, dtype=torch.uint8, device="cuda")
+        assert lib.mst_collide_poses(robot.handle, env.handle, p.data_ptr(), P, dim, out.data_ptr(), stream) == 0
+        return out
+    first = run(poses)
+    assert int((first > 1).sum()) == 0
+    assert torch.equal(run(poses), first)
+    perm = torch.randperm(P, device="cuda")
+    assert torch.equal(run(poses[perm].contiguous()), first[perm])
+
+
+def test_pipeline_answers_every_sample():
+    import torch
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(31)
+    robot, env = mst.Mesh(_soup("custom_triangle_robot")), mst.Mesh(_soup("env-scene-ltu-experiment"))
+    for K in (3, 4):
+        B, n, S = 50000, 10, 100
+        T = rng.uniform(0.5, 2.0, (B, n))
+        t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+        wp = np.zeros((B, n + 1, K))
+        wp[:, :, :3] = rng.uniform(BOUNDS_LO, BOUNDS_HI, (B, 1, 3)) + np.cumsum(rng.normal(0, 0.3, (B, n + 1, 3)), axis=1)
+        if K == 4:
+            wp[:, :, 3] = np.cumsum(rng.normal(0, 0.3, (B, n + 1)), axis=1)
+        coef, dur, info = mst.solve_batch(wp, t)
+        out = mst.PipelineResult(coef, dur, info, torch.full((B, S), 9, dtype=torch.uint8, device="cuda"),
+                                 torch.full((B,), 9, dtype=torch.uint8, device="cuda"))
+        hit, any_hit = mst.collide_trajectories(coef, dur, S, robot, env)
+        res = mst.pipeline(wp, t, S, robot, env, out=out)
+        assert int((res.hit > 1).sum()) == 0 and int((res.any_hit > 1).sum()) == 0
+        assert torch.equal(res.hit, hit) and torch.equal(res.any_hit, any_hit)
+        assert torch.equal(res.any_hit, res.hit.amax(dim=1))
