@@ -340,6 +340,17 @@ def run_ours(args):
     e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
     h2d, d2h = hp.bytes_per_trajectory()
     assert np.array_equal(host_out.any_hit.numpy(), res.any_hit.cpu().numpy())
+    # same call, results in the reference's own output format (float32 polynomial matrix)
+    del hp, host_out
+    hp32 = HostPipeline(N_SEG, K_AX, S_SAMPLES, robot, env, chunk=args.e2e_chunk, wire="pol_matrix_f32")
+    host_out32 = HostPipeline.alloc_host_result(B, N_SEG, K_AX, S_SAMPLES, wire="pol_matrix_f32")
+
+    def e2e32_step():
+        hp32.run(wp_host, t_host, host_out32)
+    for _ in range(min(args.warmup, 3)):
+        e2e32_step()
+    e2e32_ms = timed(e2e32_step, e2e_steps) / e2e_steps
+    h2d32, d2h32 = hp32.bytes_per_trajectory()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -355,7 +366,11 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
-                "chunk": hp.chunk, "note": "pinned host in/out, 3-slot copy/compute overlap"},
+                "chunk": args.e2e_chunk, "note": "pinned host in/out (FP64 coefficients), 3-slot copy/compute overlap; "
+                "PCIe-bound by the device->host copy",
+                "pol_matrix_f32_wire": {"value": world * B / (e2e32_ms * 1e-3), "ms_per_step": e2e32_ms,
+                                        "d2h_bytes_per_step": int(d2h32 * B),
+                                        "note": "same call returning path_to_pol's float32 (n,33)-style matrix"}},
         "gpu_launches": args.steps * n_chunks * lib.mst_pipeline_launch_count(B // n_chunks, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic_per_traj * B,

@@ -325,8 +325,10 @@ template <int POSE>
 __device__ __forceinline__ bool pose_near_environment(const double* pp, const MeshBounds& rbb, const MeshBounds& evb) {
   const double* root = evb.root;
   const double* T = pp;
-  // POSE 2 takes whatever quaternion the caller gave (maybe not unit): no sphere cull there
-  if (POSE != 2 && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
+  // bounding sphere first for rotated poses (cheaper than rotating the box); a translated box
+  // is exact and just as cheap, and POSE 2 takes whatever quaternion the caller gave (maybe not
+  // unit), so neither uses the sphere
+  if (POSE == 1 && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
                     T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
     return false;
   double R[9], lo[3], hi[3];

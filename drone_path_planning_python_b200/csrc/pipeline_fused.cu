@@ -88,12 +88,13 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     const int work = nb * S;
     // warp-uniform trip count: every lane stays in the loop (ballots), lanes past the end of
     // the tile are simply inactive
-    for (int base = 0; base < work; base += 32) {
+    // (trajectory, sample) of this lane, advanced by 32 samples per iteration without dividing
+    int tl = 0, s = lane;
+    for (int base = 0; base < work; base += 32, s += 32) {
       const int idx = base + lane;
       const bool active = idx < work;
-      const int cidx = active ? idx : work - 1;
-      const int tl = cidx / S;
-      const int s = cidx - tl * S;
+      while (s >= S) { s -= S; ++tl; }
+      if (!active) { tl = nb - 1; s = S - 1; }  // parked on the tile's last sample (not reported)
       const double* kn = knots + tl * (n + 1);
       const double t = __dmul_rn((double)s, dts[tl]);
       // PiecewisePolynomial.eval: first piece with t < acc + T_i, else the last one at

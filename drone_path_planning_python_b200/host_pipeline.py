@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _abi
-from .batch import Mesh, PipelineResult, pipeline
+from .batch import Mesh, PipelineResult, pack_pol_matrix, pipeline
 
 
 class HostPipeline:
@@ -21,7 +21,15 @@ class HostPipeline:
     fills the pinned host tensors of ``out`` (a ``PipelineResult`` of host tensors)."""
 
     def __init__(self, n: int, K: int, S: int, robot: Mesh, env: Mesh, chunk: int = 65536,
-                 share_time_group: int = 1, solver: str = "auto", slots: int = 3):
+                 share_time_group: int = 1, solver: str = "auto", slots: int = 3, wire: str = "f64"):
+        """``wire="f64"`` returns coefficients and durations in double precision;
+        ``wire="pol_matrix_f32"`` returns the reference's own output format instead — the
+        float32 ``(n, 1 + 8K)`` matrix ``[T | x | y | z (| yaw)]`` that ``path_to_pol`` writes and
+        publishes (scripts/drones_pols_generator.py:63-87), packed on the device
+        (``mst_pack_pol_matrix``) — which halves the device->host traffic."""
+        if wire not in ("f64", "pol_matrix_f32"):
+            raise ValueError("wire must be 'f64' or 'pol_matrix_f32'")
+        self.wire = wire
         self.dev = _abi.require_cuda()
         self.n, self.K, self.S, self.G = n, K, S, int(share_time_group)
         self.robot, self.env, self.solver = robot, env, solver
@@ -41,8 +49,15 @@ class HostPipeline:
             })
 
     @staticmethod
-    def alloc_host_result(B: int, n: int, K: int, S: int) -> PipelineResult:
+    def alloc_host_result(B: int, n: int, K: int, S: int, wire: str = "f64") -> PipelineResult:
+        """Pinned host buffers for ``run``.  With ``wire="pol_matrix_f32"`` the ``coef`` field is
+        the float32 ``[B, n, 1 + 8K]`` matrix and ``dur`` is None (column 0 of the matrix)."""
         pin = dict(pin_memory=True)
+        if wire == "pol_matrix_f32":
+            return PipelineResult(torch.empty((B, n, 1 + 8 * K), dtype=torch.float32, **pin), None,
+                                  torch.empty((B,), dtype=torch.int32, **pin),
+                                  torch.empty((B, S), dtype=torch.uint8, **pin),
+                                  torch.empty((B,), dtype=torch.uint8, **pin))
         return PipelineResult(torch.empty((B, n, K, 8), dtype=torch.float64, **pin),
                               torch.empty((B, n), dtype=torch.float64, **pin),
                               torch.empty((B,), dtype=torch.int32, **pin),
@@ -52,13 +67,16 @@ class HostPipeline:
     def bytes_per_trajectory(self):
         """(host->device, device->host) bytes moved per trajectory."""
         h2d = (self.n + 1) * self.K * 8 + (self.n + 1) * 8 / self.G
-        d2h = self.n * self.K * 64 + self.n * 8 + 4 + self.S + 1
+        if self.wire == "pol_matrix_f32":
+            d2h = self.n * (1 + 8 * self.K) * 4 + 4 + self.S + 1
+        else:
+            d2h = self.n * self.K * 64 + self.n * 8 + 4 + self.S + 1
         return h2d, d2h
 
     def run(self, wp: torch.Tensor, t: torch.Tensor, out: Optional[PipelineResult] = None) -> PipelineResult:
         B = wp.shape[0]
         if out is None:
-            out = self.alloc_host_result(B, self.n, self.K, self.S)
+            out = self.alloc_host_result(B, self.n, self.K, self.S, self.wire)
         caller = torch.cuda.current_stream()
         for i, b0 in enumerate(range(0, B, self.chunk)):
             nb = min(self.chunk, B - b0)
@@ -75,8 +93,11 @@ class HostPipeline:
                 view = PipelineResult(r.coef[:nb], r.dur[:nb], r.info[:nb], r.hit[:nb], r.any_hit[:nb])
                 pipeline(slot["wp"][:nb], slot["t"][:ng], self.S, self.robot, self.env,
                          share_time_group=self.G, solver=self.solver, out=view)
-                out.coef[b0:b0 + nb].copy_(view.coef, non_blocking=True)
-                out.dur[b0:b0 + nb].copy_(view.dur, non_blocking=True)
+                if self.wire == "pol_matrix_f32":
+                    out.coef[b0:b0 + nb].copy_(pack_pol_matrix(view.coef, view.dur), non_blocking=True)
+                else:
+                    out.coef[b0:b0 + nb].copy_(view.coef, non_blocking=True)
+                    out.dur[b0:b0 + nb].copy_(view.dur, non_blocking=True)
                 out.info[b0:b0 + nb].copy_(view.info, non_blocking=True)
                 out.hit[b0:b0 + nb].copy_(view.hit, non_blocking=True)
                 out.any_hit[b0:b0 + nb].copy_(view.any_hit, non_blocking=True)
