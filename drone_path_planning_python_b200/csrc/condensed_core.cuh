@@ -83,10 +83,10 @@ __host__ __device__ __forceinline__ Mat3 coupling_block(const RhoPow& r) {
   return b;
 }
 
-// phase 1: block LDL^T factors.  scratch element s of this group is scratch[s * stride].
-// On entry slot i (i < n) holds the duration T_i (> 0); on exit it holds rho_i = 1/T_i.
-__host__ __device__ inline void condensed_factor(int n, double* scratch, int stride) {
-  double* fac = scratch + (size_t)n * stride;
+// phase 1: block LDL^T factors.  rho[i * stride] (i < n) holds the duration T_i (> 0) on entry
+// and rho_i = 1/T_i on exit; the six factor terms of knot i go to fac[((i-1)*6 + j) * stride].
+__host__ __device__ inline void condensed_factor(int n, double* rho, double* fac, int stride) {
+  double* scratch = rho;
   RhoPow pa = rho_powers(1.0 / scratch[0]);
   scratch[0] = pa.p1;
   // Schur correction C = B_{i-1}^T S_{i-1}^{-1} B_{i-1} carried between knots (symmetric)
@@ -151,17 +151,19 @@ __host__ __device__ __forceinline__ void piece_coefficients(double w0, double dw
 
 // phase 2 (per trajectory of the group): forward elimination of the K right-hand sides.
 // wp points at this trajectory's [n+1][K] waypoints.  y is stored for the back sweep.
+// wp[i * wstride + k]: waypoint i of column k (k < K columns handled by this thread);
+// rho / fac as written by condensed_factor (stride fstride); y values go to
+// ys[((i-1)*3*K + 3*k + j) * ystride].
 template <int KC>
-__host__ __device__ inline void condensed_forward(const double* __restrict__ wp, int n, int K,
-                                                  double* scratch, int stride) {
-  const double* rho = scratch;
-  const double* fac = scratch + (size_t)n * stride;
-  double* ys = scratch + ((size_t)n + 6 * (size_t)(n - 1)) * stride;
+__host__ __device__ inline void condensed_forward(const double* __restrict__ wp, int wstride, int n, int K,
+                                                  const double* rho, const double* fac, int fstride,
+                                                  double* ys, int ystride) {
+  const int stride = fstride;
   double wprev[KC], da[KC], z1[KC], z2[KC], z3[KC];
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
     if (k < K) {
-      const double w0 = wp[k], w1 = wp[K + k];
+      const double w0 = wp[k], w1 = wp[wstride + k];
       da[k] = w1 - w0;
       wprev[k] = w1;
     }
@@ -177,15 +179,15 @@ __host__ __device__ inline void condensed_forward(const double* __restrict__ wp,
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
       if (k < K) {
-        const double wn = wp[(size_t)(i + 1) * K + k];
+        const double wn = wp[(size_t)(i + 1) * wstride + k];
         const double db = wn - wprev[k];
         wprev[k] = wn;
         // y_i = r_i - B_{i-1}^T z_{i-1}
         const double y1 = ge1 * da[k] + gs1 * db - (bp.m11 * z1[k] + bp.m21 * z2[k] + bp.m31 * z3[k]);
         const double y2 = ge2 * da[k] + gs2 * db - (bp.m12 * z1[k] + bp.m22 * z2[k] + bp.m32 * z3[k]);
         const double y3 = ge3 * da[k] + gs3 * db - (bp.m13 * z1[k] + bp.m23 * z2[k] + bp.m33 * z3[k]);
-        double* yo = ys + ((size_t)(i - 1) * 3 * K + 3 * k) * stride;
-        yo[0] = y1; yo[stride] = y2; yo[2 * (size_t)stride] = y3;
+        double* yo = ys + ((size_t)(i - 1) * 3 * K + 3 * k) * ystride;
+        yo[0] = y1; yo[ystride] = y2; yo[2 * (size_t)ystride] = y3;
         ldl3_solve(f, y1, y2, y3, z1[k], z2[k], z3[k]);
         da[k] = db;
       }
@@ -197,11 +199,10 @@ __host__ __device__ inline void condensed_forward(const double* __restrict__ wp,
 // phase 3: back sweep knot n-1 .. 1; after knot i is known piece i is complete and handed
 // to `emit(piece, k, c[8], rho_i)`; piece 0 last.  (Pieces therefore arrive in DESCENDING order.)
 template <int KC, class Emit>
-__host__ __device__ inline void condensed_backward(const double* __restrict__ wp, int n, int K,
-                                                   const double* scratch, int stride, Emit&& emit) {
-  const double* rho = scratch;
-  const double* fac = scratch + (size_t)n * stride;
-  const double* ys = scratch + ((size_t)n + 6 * (size_t)(n - 1)) * stride;
+__host__ __device__ inline void condensed_backward(const double* __restrict__ wp, int wstride, int n, int K,
+                                                   const double* rho, const double* fac, int fstride,
+                                                   const double* ys, int ystride, Emit&& emit) {
+  const int stride = fstride;
   double xv[KC], xa[KC], xj[KC];  // state at knot i+1
 #pragma unroll
   for (int k = 0; k < KC; ++k) xv[k] = xa[k] = xj[k] = 0.0;
@@ -215,10 +216,10 @@ __host__ __device__ inline void condensed_backward(const double* __restrict__ wp
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
         if (k < K) {
-          const double* yo = ys + ((size_t)(i - 1) * 3 * K + 3 * k) * stride;
+          const double* yo = ys + ((size_t)(i - 1) * 3 * K + 3 * k) * ystride;
           const double b1 = yo[0] - (b.m11 * xv[k] + b.m12 * xa[k] + b.m13 * xj[k]);
-          const double b2 = yo[stride] - (b.m21 * xv[k] + b.m22 * xa[k] + b.m23 * xj[k]);
-          const double b3 = yo[2 * (size_t)stride] - (b.m31 * xv[k] + b.m32 * xa[k] + b.m33 * xj[k]);
+          const double b2 = yo[ystride] - (b.m21 * xv[k] + b.m22 * xa[k] + b.m23 * xj[k]);
+          const double b3 = yo[2 * (size_t)ystride] - (b.m31 * xv[k] + b.m32 * xa[k] + b.m33 * xj[k]);
           ldl3_solve(f, b1, b2, b3, nv[k], na[k], nj[k]);
         }
       }
@@ -229,7 +230,7 @@ __host__ __device__ inline void condensed_backward(const double* __restrict__ wp
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
       if (k < K) {
-        const double w0 = wp[(size_t)i * K + k], w1 = wp[(size_t)(i + 1) * K + k];
+        const double w0 = wp[(size_t)i * wstride + k], w1 = wp[(size_t)(i + 1) * wstride + k];
         double c[MST_NCOEF];
         piece_coefficients(w0, w1 - w0, nv[k], na[k], nj[k], xv[k], xa[k], xj[k], rh, c);
         emit(i, k, c, rh);

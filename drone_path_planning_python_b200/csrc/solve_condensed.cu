@@ -6,6 +6,8 @@
 // for time groups whose duration spread allows it; every other group is appended to a
 // device-side list that the banded pivoted-LU kernel consumes right after (no host sync).
 #include "condensed_core.cuh"
+#include <stdlib.h>
+
 #include "stage.cuh"
 
 namespace mst {
@@ -95,14 +97,16 @@ condensed_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
         continue;
       }
     }
+    double* fac = scratch + (size_t)n * stride;
+    double* ys = scratch + ((size_t)n + 6 * (size_t)(n - 1)) * stride;
     for (int i = 0; i < n; ++i) scratch[(size_t)i * stride] = tg[i + 1] - tg[i];
-    condensed_factor(n, scratch, stride);
+    condensed_factor(n, scratch, fac, stride);
     for (int d = 0; d < G; ++d) {
       const size_t traj = (size_t)g * G + d;
       const double* wpd = STAGED ? wp_tile + (size_t)threadIdx.x * (n + 1) * K : wp + traj * (size_t)(n + 1) * K;
-      condensed_forward<KC>(wpd, n, K, scratch, stride);
+      condensed_forward<KC>(wpd, K, n, K, scratch, fac, stride, ys, stride);
       double* cd = coef + traj * (size_t)n * K * MST_NCOEF;
-      condensed_backward<KC>(wpd, n, K, scratch, stride,
+      condensed_backward<KC>(wpd, K, n, K, scratch, fac, stride, ys, stride,
                              [&](int piece, int k, const double* c, double) {
                                double2* dst = reinterpret_cast<double2*>(cd + ((size_t)piece * K + k) * MST_NCOEF);
                                dst[0] = make_double2(c[0], c[1]);
@@ -115,6 +119,101 @@ condensed_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Lane-per-column variant.  One LANE per right-hand side column (trajectory d of the group,
+// axis k): a warp holds GPW = 32 / (G*K) time groups, the LDL^T factors of a group live once in
+// shared memory (written by the group's first lane, read by all its columns as broadcasts) and
+// every lane keeps only its own column's forward values (3 per knot).  Shared memory per
+// trajectory is the same as with one thread per group, but it now feeds G*K times as many
+// threads: 14 warps per SM instead of 4 at n = 10, K = 3, which is what the latency-bound
+// recurrences need (profiles/README.md).  The group's factorisation is not repeated per
+// column; the price is that the other columns' lanes idle during it.  The lanes of one
+// trajectory write adjacent 64-byte coefficient rows and read adjacent waypoint values.
+// Inputs of the warp's groups are one contiguous range each: copied into shared memory with
+// coalesced loads before use.
+template <int dummy>
+__global__ void __launch_bounds__(128)
+condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps, int groups, int n,
+                      int K, int G, int force, double* __restrict__ coef, double* __restrict__ dur,
+                      int* __restrict__ info, int* __restrict__ list, int* __restrict__ list_count) {
+  extern __shared__ __align__(16) double sm[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int R = G * K;        // columns per group
+  const int GPW = 32 / R;     // groups per warp
+  const int gl = lane / R;    // group slot of this lane
+  const int col = lane - gl * R;
+  const int d = col / K, k = col - d * K;
+  const bool lane_used = gl < GPW;
+  // per-warp shared memory: rho[n][GPW] | fac[6(n-1)][GPW] | y[3(n-1)][32] | t[GPW][n+1] | wp[GPW*G][n+1][K]
+  const size_t per_warp = (size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) * (1 + R);
+  double* wrho = sm + warp * per_warp;
+  double* wfac = wrho + (size_t)GPW * n;
+  double* wy = wfac + (size_t)GPW * 6 * (n - 1);
+  double* wt = wy + 32 * (size_t)(3 * (n - 1));
+  double* ww = wt + (size_t)GPW * (n + 1);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+  const long long sets = ((long long)groups + GPW - 1) / GPW;
+  for (long long set = blockIdx.x * (long long)warps + warp; set < sets; set += (long long)gridDim.x * warps) {
+    const long long g0 = set * GPW;
+    const int cnt = (int)min((long long)GPW, groups - g0);
+    __syncwarp();  // the previous set's tiles are no longer read
+    for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = tstamps[(size_t)g0 * (n + 1) + i];
+    for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[i] = wp[(size_t)g0 * (n + 1) * R + i];
+    __syncwarp();
+    const bool mine = lane_used && gl < cnt;
+    const long long g = g0 + gl;
+    const double* tg = wt + (size_t)gl * (n + 1);
+    // classification and factorisation by the group's first column
+    int cls = 0;
+    if (mine && col == 0) {
+      double Tmin, Tmax;
+      cls = classify_times(tg, n, &Tmin, &Tmax);
+      if (cls == 1 && force > 0 && Tmin > 0.0 && tg[0] == 0.0) cls = 0;            // forced: solve anyway
+      else if (cls == 1 && force > 0) cls = !(Tmin > 0.0) ? 4 : 5;                 // forced but impossible
+      if (cls == 1 || (cls == 0 && force < 0)) { cls = 1; list[atomicAdd(list_count, 1)] = (int)g; }
+      if (cls == 0) {
+        double* rho = wrho + gl;
+        for (int i = 0; i < n; ++i) rho[(size_t)i * GPW] = tg[i + 1] - tg[i];
+        condensed_factor(n, rho, wfac + gl, GPW);
+      }
+    }
+    cls = __shfl_sync(FULL, cls, lane_used ? gl * R : 0);
+    __syncwarp();
+    if (!mine) continue;
+    const size_t traj = (size_t)g * G + d;
+    if (k == 0) {
+      double* dd = dur + traj * n;
+      for (int i = 0; i < n; ++i) dd[i] = tg[i + 1] - tg[i];
+    }
+    if (cls == 1) continue;  // the pivoted solver will write coefficients and status
+    double* cd = coef + traj * (size_t)n * K * MST_NCOEF + (size_t)k * MST_NCOEF;
+    if (cls != 0) {
+      for (int i = 0; i < n; ++i)
+        for (int e = 0; e < MST_NCOEF; ++e) cd[(size_t)i * K * MST_NCOEF + e] = qnan;
+      if (k == 0) info[traj] = cls == 2 ? MST_INFO_DECREASING : (cls == 3 ? MST_INFO_NONFINITE : (cls == 4 ? 1 : MST_INFO_DECLINED));
+      continue;
+    }
+    const double* wcol = ww + ((size_t)gl * G + d) * (n + 1) * K + k;
+    condensed_forward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
+    condensed_backward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32,
+                          [&](int piece, int, const double* c, double) {
+                            double2* dst = reinterpret_cast<double2*>(cd + (size_t)piece * K * MST_NCOEF);
+                            dst[0] = make_double2(c[0], c[1]);
+                            dst[1] = make_double2(c[2], c[3]);
+                            dst[2] = make_double2(c[4], c[5]);
+                            dst[3] = make_double2(c[6], c[7]);
+                          });
+    if (k == 0) info[traj] = MST_INFO_OK;
+  }
+}
+
+static size_t cols_smem_per_warp(int n, int K, int G) {
+  const int R = G * K, GPW = 32 / R;
+  return sizeof(double) * ((size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) * (1 + R));
+}
+
 int launch_condensed(const double* wp, const double* t, int groups, int n, int K, int G, int force,
                      double* coef, double* dur, int* info, int* list, int* list_count,
                      cudaStream_t stream) {
@@ -124,6 +223,25 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
   }
   cudaError_t e = cudaMemsetAsync(list_count, 0, sizeof(int), stream);
   if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  static const bool use_cols = getenv("MST_CONDENSED_THREAD_PER_GROUP") == nullptr;
+  if (use_cols && G * K <= 32 && n >= 1) {
+    const size_t per_warp = cols_smem_per_warp(n, K, G);
+    // warps per CTA: small CTAs pack the SM's shared memory best (warps are independent)
+    const int wpb = 2 * per_warp + 64 <= MST_MAX_SMEM ? 2 : 1;
+    if (wpb * per_warp + 64 <= MST_MAX_SMEM) {
+      const int GPW = 32 / (G * K);
+      const long long sets = ((long long)groups + GPW - 1) / GPW;
+      const int rc = allow_dynamic_smem((const void*)condensed_cols_kernel<0>, wpb * per_warp);
+      if (rc != MST_OK) return rc;
+      long long blocks = (sets + wpb - 1) / wpb;
+      const long long cap = (long long)MST_SM_COUNT * 16;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      condensed_cols_kernel<0><<<(unsigned)blocks, 32 * wpb, wpb * per_warp, stream>>>(wp, t, groups, n, K, G, force, coef,
+                                                                                       dur, info, list, list_count);
+      return check_launch();
+    }
+  }
   const int Kc = K > 4 ? 4 : K;
   const size_t scratch_per_thread = sizeof(double) * (size_t)condensed_slots(n, Kc);
   // staged input tiles (G == 1, 16-byte aligned slices for any tile start)

@@ -21,8 +21,11 @@ extern "C" int hostcheck_condensed(const double* wp, const double* t, int groups
     const int cls = classify_times(tg, n, &Tmin, &Tmax);
     cls_out[g] = cls;
     if (cls >= 2 || (cls == 1 && (!force || !(Tmin > 0.0) || tg[0] != 0.0))) continue;
-    for (int i = 0; i < n; ++i) scratch[i] = tg[i + 1] - tg[i];
-    condensed_factor(n, scratch.data(), 1);
+    double* rho = scratch.data();
+    double* fac = rho + n;
+    double* ys = fac + 6 * (n - 1);
+    for (int i = 0; i < n; ++i) rho[i] = tg[i + 1] - tg[i];
+    condensed_factor(n, rho, fac, 1);
     for (int d = 0; d < G; ++d) {
       const size_t traj = (size_t)g * G + d;
       const double* wpd = wp + traj * (size_t)(n + 1) * K;
@@ -31,11 +34,11 @@ extern "C" int hostcheck_condensed(const double* wp, const double* t, int groups
         for (int e = 0; e < MST_NCOEF; ++e) cd[((size_t)piece * K + k) * MST_NCOEF + e] = c[e];
       };
       if (K <= 3) {
-        condensed_forward<3>(wpd, n, K, scratch.data(), 1);
-        condensed_backward<3>(wpd, n, K, scratch.data(), 1, emit);
+        condensed_forward<3>(wpd, K, n, K, rho, fac, 1, ys, 1);
+        condensed_backward<3>(wpd, K, n, K, rho, fac, 1, ys, 1, emit);
       } else {
-        condensed_forward<4>(wpd, n, K, scratch.data(), 1);
-        condensed_backward<4>(wpd, n, K, scratch.data(), 1, emit);
+        condensed_forward<4>(wpd, K, n, K, rho, fac, 1, ys, 1);
+        condensed_backward<4>(wpd, K, n, K, rho, fac, 1, ys, 1, emit);
       }
     }
   }

@@ -47,8 +47,10 @@ def test_calculate_trajectory4d_matches_reference_output(dropin, golden_dir):
         # consumers call .reshape((1, 8)) on p (scripts/drones_pols_generator.py:72)
         assert pols_coeffs[0][0].p.reshape((1, 8)).shape == (1, 8)
         pieces, total = calculate_trajectory1D(pts, o.Waypoint.WP_TYPE_Y)
-        assert np.array_equal(np.stack([p.p.reshape(8) for p in pieces]),
-                              np.stack([p.p.reshape(8) for p in pols_coeffs[1]]))
+        one = np.stack([p.p.reshape(8) for p in pieces])
+        four = np.stack([p.p.reshape(8) for p in pols_coeffs[1]])
+        # the same axis solved alone or with its siblings (kernel tiling may differ: last-bit level)
+        assert np.abs(one - four).max() <= 1e-12 * np.abs(four).max()
 
 
 def test_reference_exceptions(dropin):
