@@ -49,7 +49,6 @@ int launch_poly_derivative(const double* p, int count, int len, double* out, cud
 int launch_poly_terms(const double* p, const double* t, int count, int len, double* out, cudaStream_t stream);
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream);
-int launch_any_hit(const uint8_t* hit, int B, int S, uint8_t* any_hit, cudaStream_t stream);
 int launch_formation(const double* rb, int F, int m, int pose_dim, const double* off, int D, int K,
                      double* wp, cudaStream_t stream);
 

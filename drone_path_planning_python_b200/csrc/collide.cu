@@ -8,11 +8,9 @@
 // translated by -P1, and is separated on an axis only when min1 > max2 or min2 > max1
 // (strict: touching counts as a hit).
 //
-// Layout: both meshes are staged once per CTA in shared memory (<= 56 triangles x 72 B
-// for every shipped mesh) together with the environment's per-triangle AABBs; one thread
-// walks one pose.  Culling is conservative and exact-safe: bounding sphere of the robot
-// vs the environment's root box, then triangle AABB vs triangle AABB with non-strict
-// comparisons, then the SAT with early exit on the first separating axis.
+// Layout: both meshes travel as one contiguous image each (mesh_image.cuh) that a CTA stages
+// into shared memory with one bulk (TMA) copy; poses run through the warp-level collision
+// engine of collide_core.cuh (root-box cull, pose ring, per-lane cursors with early exit).
 #include <stdlib.h>
 #include <string.h>
 
@@ -69,19 +67,6 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
     ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
-// any_hit[b] = OR_s hit[b][s]; one warp per trajectory
-__global__ void any_hit_kernel(const uint8_t* __restrict__ hit, int B, int S, uint8_t* __restrict__ any_hit) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long b = warp; b < B; b += nwarps) {
-    int any = 0;
-    for (int s = lane; s < S; s += 32) any |= hit[b * S + s];
-    any = __reduce_or_sync(0xffffffffu, any);
-    if (lane == 0) any_hit[b] = any ? 1 : 0;
-  }
-}
-
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;
@@ -97,15 +82,6 @@ int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pos
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, 128, smem, stream>>>(robot->d_image, robot->layout, robot->bounds, env->d_image,
                                                 env->layout, env->bounds, pose, P, hit);
-  return check_launch();
-}
-
-int launch_any_hit(const uint8_t* hit, int B, int S, uint8_t* any_hit, cudaStream_t stream) {
-  if (B == 0) return MST_OK;
-  long long blocks = ((long long)B * 32 + 255) / 256;
-  const long long cap = (long long)MST_SM_COUNT * 16;
-  if (blocks > cap) blocks = cap;
-  any_hit_kernel<<<(unsigned)blocks, 256, 0, stream>>>(hit, B, S, any_hit);
   return check_launch();
 }
 
