@@ -24,7 +24,7 @@ int allow_dynamic_smem(const void* kernel, size_t dynamic_bytes) {
   cudaError_t e = cudaFuncGetAttributes(&attr, kernel);
   if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
   if (attr.sharedSizeBytes + dynamic_bytes > MST_MAX_SMEM) return MST_ERR_TOO_LARGE;
-  if (dynamic_bytes <= 48 * 1024) return MST_OK;  // within the default limit
+  if (attr.sharedSizeBytes + dynamic_bytes <= 48 * 1024) return MST_OK;  // within the default limit
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynamic_bytes);
   if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
   return MST_OK;
@@ -137,8 +137,12 @@ extern "C" int mst_solve_batch(const double* wp, const double* t, int B, int n, 
   if (!wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
   const int groups = B / G;
   cudaStream_t st = (cudaStream_t)stream;
-  if (banded_lu_smem_per_warp(n, G * K) > MST_MAX_SMEM && solver != MST_SOLVER_CONDENSED)
-    return MST_ERR_TOO_LARGE;
+  const bool banded_fits = banded_lu_smem_per_warp(n, G * K) <= MST_MAX_SMEM;
+  if (!banded_fits && solver == MST_SOLVER_BANDED_LU) return MST_ERR_TOO_LARGE;
+  // trajectories too long for the pivoted solver's on-chip band: AUTO degrades to the condensed
+  // solver alone, and a group it has to decline is reported through info[] (MST_INFO_DECLINED /
+  // singular) instead of being solved
+  if (!banded_fits && solver == MST_SOLVER_AUTO) solver = MST_SOLVER_CONDENSED;
   if (solver == MST_SOLVER_BANDED_LU)
     return launch_banded_lu(wp, t, groups, n, K, G, nullptr, nullptr, coef, dur, info, st);
   if (!workspace) return MST_ERR_INVALID;
