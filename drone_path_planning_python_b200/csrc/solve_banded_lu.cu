@@ -116,50 +116,54 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
     __syncwarp();
 
     // ---- banded LU with partial pivoting, right-hand sides carried along --------------
-    int ju = 0, singular_at = 0;
+    // Lane l owns column j + l of the active window (l <= KV) — its rows j..j+km are contiguous
+    // in the band and a stride of LD - 1 = 27 doubles apart between lanes (conflict free) — and
+    // lanes KV+1.. own one right-hand side each.  EVERY lane reads column j (broadcast loads) and
+    // repeats the pivot search and the multipliers in registers, so a step needs no reduction,
+    // no broadcast and a single warp barrier.  (First version: pivot search by shuffle
+    // reduction, swap / scale / rank-1 update as separate phases with the 150 window elements
+    // spread over the lanes: 6 barriers and ~3x the instructions per step.)
+    int singular_at = 0;
     for (int j = 0; j < N; ++j) {
       const int km = min(KL, N - 1 - j);
-      double* colj = AB + (size_t)j * LD;
-      double v = (lane <= km) ? fabs(colj[KV + lane]) : -1.0;
-      int jp = lane;
-      #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_xor_sync(FULL, v, off);
-        const int oi = __shfl_xor_sync(FULL, jp, off);
-        if (ov > v || (ov == v && oi < jp)) { v = ov; jp = oi; }
+      const double* colj = AB + (size_t)j * LD + KV;
+      double a[KL + 1];
+#pragma unroll
+      for (int r = 0; r <= KL; ++r) a[r] = r <= km ? colj[r] : 0.0;
+      int jp = 0;
+      double best = fabs(a[0]);
+#pragma unroll
+      for (int r = 1; r <= KL; ++r) {
+        const double v = fabs(a[r]);
+        if (v > best) { best = v; jp = r; }  // first maximum, as LAPACK's idamax
       }
-      if (v > 0.0) {
-        ju = max(ju, min(j + KU + jp, N - 1));
-        const int ncol = ju - j;
-        if (jp != 0) {
-          for (int cc = lane; cc <= ncol; cc += 32) {
-            double* p = AB + (size_t)(j + cc) * LD + KV - cc;
-            const double a = p[0]; p[0] = p[jp]; p[jp] = a;
+      if (best > 0.0) {
+        double piv = a[0];
+#pragma unroll
+        for (int r = 1; r <= KL; ++r) if (r == jp) { piv = a[r]; a[r] = a[0]; }
+        const double rinv = 1.0 / piv;
+        // my column of the window, or my right-hand side
+        double* ptr = nullptr;
+        const int c = j + lane;
+        if (lane <= KV && c < N) ptr = AB + (size_t)c * LD + KV - lane;
+        for (int q = lane - (KV + 1); q < R; q += 32 - (KV + 1)) {
+          if (q >= 0) ptr = Bs + (size_t)q * N + j;
+          if (ptr) {
+            const double x0 = ptr[0], xp = ptr[jp];
+            ptr[jp] = x0;   // row swap (a no-op when jp == 0)
+            ptr[0] = xp;
+#pragma unroll
+            for (int r = 1; r <= KL; ++r)
+              if (r <= km) ptr[r] = ptr[r] - (a[r] * rinv) * xp;
           }
-          for (int r = lane; r < R; r += 32) {
-            double* b = Bs + (size_t)r * N + j;
-            const double a = b[0]; b[0] = b[jp]; b[jp] = a;
-          }
-          __syncwarp();
+          if (q < 0) break;  // matrix lanes have exactly one column
         }
-        const double pivot = colj[KV];
-        if (lane >= 1 && lane <= km) colj[KV + lane] = colj[KV + lane] / pivot;
-        __syncwarp();
-        const int tot = km * ncol;
-        for (int e = lane; e < tot; e += 32) {
-          const int c = e / km + 1, r = e - (c - 1) * km + 1;
-          double* pc = AB + (size_t)(j + c) * LD + KV - c;
-          pc[r] -= colj[KV + r] * pc[0];
-        }
-        for (int e = lane; e < km * R; e += 32) {
-          const int rr = e / km, r = e - rr * km + 1;
-          double* b = Bs + (size_t)rr * N + j;
-          b[r] -= colj[KV + r] * b[0];
-        }
-        __syncwarp();
+        // U(j, j) must read back as the pivot (lane 0 just wrote xp = piv there) and the
+        // multipliers below it are not kept: the right-hand sides were updated in the same step
       } else if (singular_at == 0) {
         singular_at = j + 1;
       }
+      __syncwarp();
     }
 
     // ---- back substitution with the banded upper factor -------------------------------
