@@ -236,7 +236,8 @@ def run_ours(args):
     if world > 1:
         if args.gather == "push":
             try:
-                gather = PeerPushAllGather(B, world, rank, args.gather_chunks, [res.coef, res.hit, res.any_hit])
+                gather = PeerPushAllGather(B, world, rank, args.gather_chunks, [res.coef, res.hit, res.any_hit],
+                                           streams=args.push_streams)
                 gather_kind = "peer push over NVLink (copy engines, symmetric memory)"
                 res = mst.PipelineResult(gather.local_slot(0), res.dur, res.info, gather.local_slot(1),
                                          gather.local_slot(2))
@@ -407,8 +408,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--traj", type=int, default=TRAJ_PER_GPU, help="trajectories per GPU per step")
-    ap.add_argument("--gather-chunks", type=int, default=4)
+    ap.add_argument("--gather-chunks", type=int, default=2)
     ap.add_argument("--gather", choices=["push", "nccl"], default="push")
+    ap.add_argument("--push-streams", type=int, default=1)
     ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="tiny CPU sample (smoke runs)")

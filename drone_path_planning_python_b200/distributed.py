@@ -95,7 +95,7 @@ class PeerPushAllGather:
     """
 
     def __init__(self, count: int, world: int, rank: int, chunks: int, templates: Sequence[torch.Tensor],
-                 group: int = 1):
+                 group: int = 1, streams: int = 1):
         import torch.distributed._symmetric_memory as symm
         self.count, self.world, self.rank = count, world, rank
         self.plan = chunk_plan(count, chunks, group)
@@ -108,10 +108,9 @@ class PeerPushAllGather:
             self.buffers.append(buf)
             self.handles.append(hdl)
             self.peers.append([buf if p == rank else hdl.get_buffer(p, shape, t.dtype) for p in range(world)])
-        # ONE side stream: pushing to all peers concurrently from per-peer streams was measured
-        # slower at 8 GPUs (33.9 vs 27.6 ms per step) - the staggered order below already keeps
-        # every link busy without oversubscribing the switch
-        self.comm = torch.cuda.Stream(device=templates[0].device)
+        # few side streams: pushing to all 7 peers concurrently from per-peer streams was measured
+        # slower at 8 GPUs than one stream (33.9 vs 27.6 ms per step); see profiles/r1_scaling.md
+        self.comm = [torch.cuda.Stream(device=templates[0].device) for _ in range(max(1, min(streams, world - 1)))]
         self.out = self.buffers
 
     def local_slot(self, k: int, lo: int = 0, hi: int = None) -> torch.Tensor:
@@ -127,12 +126,14 @@ class PeerPushAllGather:
         base = self.rank * self.count
         for lo, hi in self.plan:
             compute_chunk(lo, hi)
-            self.comm.wait_stream(cur)
-            with torch.cuda.stream(self.comm):
-                for shift in range(1, self.world):   # staggered so the links are loaded evenly
-                    p = (self.rank + shift) % self.world
+            for side in self.comm:
+                side.wait_stream(cur)
+            for shift in range(1, self.world):       # staggered so the links are loaded evenly
+                p = (self.rank + shift) % self.world
+                with torch.cuda.stream(self.comm[(shift - 1) % len(self.comm)]):
                     for k, buf in enumerate(self.buffers):
                         self.peers[k][p][base + lo:base + hi].copy_(buf[base + lo:base + hi], non_blocking=True)
-        cur.wait_stream(self.comm)
+        for side in self.comm:
+            cur.wait_stream(side)
         self.handles[0].barrier(channel=1)          # every peer's pushes into this buffer have landed
         return self.out
