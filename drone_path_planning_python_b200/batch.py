@@ -111,6 +111,20 @@ def solve_batch(wp, t, share_time_group: int = 1, solver: str = "auto"
     return coef, dur, info
 
 
+def snap_cost(coef, dur) -> torch.Tensor:
+    """``cost[B]`` = sum over pieces and axes of the integral of the squared 4th derivative
+    (the objective whose optimality system the reference solves; an extension for
+    time-allocation searches)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    coef = _f64(coef, dev)
+    dur = _f64(dur, dev)
+    B, n, K, _ = coef.shape
+    cost = torch.empty((B,), dtype=torch.float64, device=dev)
+    _abi.check(lib.mst_snap_cost(_ptr(coef), _ptr(dur), B, n, K, _ptr(cost), _stream_ptr()), "mst_snap_cost")
+    return cost
+
+
 # --------------------------------------------------------------------------- a8
 def pack_pol_matrix(coef, dur) -> torch.Tensor:
     """``coef[B, n, K, 8]``, ``dur[B, n]`` -> float32 ``[B, n, 1 + 8K]`` rows

@@ -45,6 +45,7 @@ int launch_flat(const double* coef, const double* dur, int B, int n, const doubl
                 int S, int mode, double* out, uint8_t* status, cudaStream_t stream);
 int launch_time_power(const double* t, int count, double* rows, cudaStream_t stream);
 int launch_pack_matrix(const double* coef, const double* dur, long long rows, int K, float* out, cudaStream_t stream);
+int launch_snap_cost(const double* coef, const double* dur, int B, int n, int K, double* cost, cudaStream_t stream);
 int launch_poly_derivative(const double* p, int count, int len, double* out, cudaStream_t stream);
 int launch_poly_terms(const double* p, const double* t, int count, int len, double* out, cudaStream_t stream);
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
@@ -110,6 +111,13 @@ extern "C" int mst_poly_terms_at_t(const double* p, const double* t, int count, 
   if (count == 0) return MST_OK;
   if (!p || !t || !out) return MST_ERR_INVALID;
   return launch_poly_terms(p, t, count, len, out, (cudaStream_t)stream);
+}
+
+extern "C" int mst_snap_cost(const double* coef, const double* dur, int B, int n, int K, double* cost, void* stream) {
+  if (B < 0 || n < 1 || K < 1) return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!coef || !dur || !cost) return MST_ERR_INVALID;
+  return launch_snap_cost(coef, dur, B, n, K, cost, (cudaStream_t)stream);
 }
 
 extern "C" int mst_pack_pol_matrix(const double* coef, const double* dur, int B, int n, int K, float* out,

@@ -232,6 +232,40 @@ int launch_pack_matrix(const double* coef, const double* dur, long long rows, in
   return check_launch();
 }
 
+// Snap cost J = sum over pieces and axes of int_0^T (d^4 p / dt^4)^2 dt = c^T Q(T) c, Q the snap
+// Hessian of the monomial basis: Q[i][j] = i!/(i-4)! * j!/(j-4)! * T^(i+j-7) / (i+j-7), i,j >= 4.
+// Not computed anywhere in the reference (its square system is the optimality system of exactly
+// this cost); provided for time-allocation searches over re-solves (BASELINE config 3).
+// One thread per trajectory.
+__global__ void __launch_bounds__(128)
+snap_cost_kernel(const double* __restrict__ coef, const double* __restrict__ dur, int B, int n, int K,
+                 double* __restrict__ cost) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    double total = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double T = dur[(size_t)b * n + i];
+      const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2, T5 = T4 * T, T6 = T3 * T3, T7 = T6 * T;
+      for (int k = 0; k < K; ++k) {
+        const double2* row = reinterpret_cast<const double2*>(coef + (((size_t)b * n + i) * K + k) * MST_NCOEF);
+        const double2 c45 = __ldg(row + 2), c67 = __ldg(row + 3);
+        // fourth derivative: a0 + a1 t + a2 t^2 + a3 t^3
+        const double a0 = 24.0 * c45.x, a1 = 120.0 * c45.y, a2 = 360.0 * c67.x, a3 = 840.0 * c67.y;
+        total += a0 * a0 * T + a0 * a1 * T2 + (2.0 * a0 * a2 + a1 * a1) * (T3 / 3.0) + (a0 * a3 + a1 * a2) * (T4 * 0.5) +
+                 (2.0 * a1 * a3 + a2 * a2) * (T5 / 5.0) + a2 * a3 * (T6 / 3.0) + a3 * a3 * (T7 / 7.0);
+      }
+    }
+    cost[b] = total;
+  }
+}
+
+int launch_snap_cost(const double* coef, const double* dur, int B, int n, int K, double* cost, cudaStream_t stream) {
+  if (B <= 0) return MST_OK;
+  long long g = ((long long)B + 127) / 128;
+  if (g > (long long)MST_SM_COUNT * 16) g = (long long)MST_SM_COUNT * 16;
+  snap_cost_kernel<<<(unsigned)g, 128, 0, stream>>>(coef, dur, B, n, K, cost);
+  return check_launch();
+}
+
 static unsigned grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)MST_SM_COUNT * 32;

@@ -122,6 +122,16 @@ int mst_solve_batch(const double* wp, const double* t, int B, int n, int K,
                     int* info, void* workspace, void* stream);
 
 /*
+ * Snap cost of solved trajectories: cost[b] = sum over pieces and axes of the integral of the
+ * squared 4th derivative over the piece = c^T Q(T) c.  An extension: the reference never
+ * evaluates the cost whose optimality system it solves
+ * (src/optimizations/calculatingTrajectories.py:13-35); it is the objective of time-allocation
+ * searches over re-solves (BASELINE config 3).
+ *   coef [B][n][K][8], dur [B][n]  ->  cost [B]
+ */
+int mst_snap_cost(const double* coef, const double* dur, int B, int n, int K, double* cost, void* stream);
+
+/*
  * Polynomial-piece matrix — the wire format path_to_pol writes to CSV and publishes
  * (scripts/drones_pols_generator.py:63-87): per piece one float32 row
  * [T | x0..x7 | y0..y7 | z0..z7 | yaw0..yaw7].

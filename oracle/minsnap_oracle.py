@@ -301,3 +301,17 @@ def formation_waypoints(rb_poses, offsets):
             out[d, i, :3] = quat_rotate(q, offsets[d]) + rb_poses[i, :3]
             out[d, i, 3] = rb_poses[i, 3]
     return out
+
+
+# --------------------------------------------------------------------------- extension
+def snap_cost(coef, durations):
+    """Integral of the squared 4th derivative over all pieces and axes of ``coef[n, K, 8]`` -
+    the objective whose optimality system the reference's square system is (the reference never
+    evaluates it).  Exact polynomial integration with numpy.polynomial."""
+    from numpy.polynomial import polynomial as P
+    total = 0.0
+    for i, T in enumerate(durations):
+        for k in range(coef.shape[1]):
+            d4 = P.polyder(np.asarray(coef[i, k], dtype=np.float64), 4)
+            total += P.polyval(float(T), P.polyint(P.polymul(d4, d4)))
+    return float(total)

@@ -219,3 +219,28 @@ def test_shipped_pol_matrices_reproduce_in_position_space(golden_dir):
                                     packed[None, :, 0].astype(np.float64), ts=ts).cpu().numpy()[0]
             theirs = mst.sample_batch(c[None], T[None], ts=ts).cpu().numpy()[0]
             assert np.abs(ours[:, :3] - theirs[:, :3]).max() < 1e-6, (name, solver)
+
+
+def test_snap_cost_extension():
+    """Extension: the snap cost c^T Q c of the solution against exact polynomial integration, its
+    T^-7 scaling under a uniform re-timing, and determinism."""
+    from oracle import minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(12)
+    B, n, K = 40, 6, 3
+    T = rng.uniform(0.5, 2.0, (B, n))
+    t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+    wp = np.cumsum(rng.normal(0, 0.3, (B, n + 1, K)), axis=1)
+    coef, dur, info = mst.solve_batch(wp, t)
+    cost = mst.snap_cost(coef, dur).cpu().numpy()
+    for b in range(0, B, 7):
+        ref = mo.snap_cost(coef[b].cpu().numpy(), dur[b].cpu().numpy())
+        assert abs(cost[b] - ref) <= 1e-10 * abs(ref)
+    # re-timing the same waypoints changes the cost (what a time-allocation search exploits) ...
+    coef2, dur2, _ = mst.solve_batch(wp, t * 1.25)
+    cost2 = mst.snap_cost(coef2, dur2).cpu().numpy()
+    assert np.allclose(cost2, cost / 1.25 ** 7, rtol=1e-9)          # J scales like T^-7
+    # ... and among interpolants of the same waypoints, another time allocation of equal total
+    # duration is generally worse or better: the optimum over T is what config 3 searches for
+    worse, _, _ = mst.solve_batch(wp + 0.0, t)      # same solve: cost identical (determinism)
+    assert np.array_equal(mst.snap_cost(worse, dur).cpu().numpy(), cost)
