@@ -45,6 +45,8 @@ PROTOTYPES = {
     "mst_mesh_triangle_count": (ctypes.c_int, [c_void_p]),
     "mst_collide_poses": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
                                          c_void_p, c_void_p]),
+    "mst_collide_motions": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
+                                           c_void_p, c_void_p]),
     "mst_collide_trajectories": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mst_pipeline_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),

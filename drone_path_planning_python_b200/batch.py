@@ -268,6 +268,23 @@ def collide_poses(robot: Mesh, env: Mesh, poses) -> torch.Tensor:
     return hit
 
 
+def collide_motions(robot: Mesh, env: Mesh, state_a, state_b, steps: int) -> torch.Tensor:
+    """``state_a[M, 4]``, ``state_b[M, 4]`` (x, y, z, yaw) -> ``invalid[M]`` uint8: 1 iff one of the
+    ``steps`` states interpolated at fractions ``j/steps`` (j = 1..steps) collides.  All
+    interpolated states of all candidate motions in one launch."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    a = _f64(state_a, dev)
+    b = _f64(state_b, dev)
+    if a.shape != b.shape or a.dim() != 2 or a.shape[1] != 4:
+        raise ValueError("states must be [M, 4] (x, y, z, yaw)")
+    M = a.shape[0]
+    invalid = torch.empty((M,), dtype=torch.uint8, device=dev)
+    rc = lib.mst_collide_motions(robot.handle, env.handle, _ptr(a), _ptr(b), M, int(steps), _ptr(invalid), _stream_ptr())
+    _abi.check(rc, "mst_collide_motions")
+    return invalid
+
+
 def collide_trajectories(coef, dur, S: int, robot: Mesh, env: Mesh):
     """Sample ``S`` uniform times of every trajectory and collision-check the robot mesh placed
     there; returns ``hit[B, S]``, ``any_hit[B]`` (the pipeline's second kernel on its own)."""

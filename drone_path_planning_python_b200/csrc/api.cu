@@ -50,6 +50,8 @@ int launch_poly_derivative(const double* p, int count, int len, double* out, cud
 int launch_poly_terms(const double* p, const double* t, int count, int len, double* out, cudaStream_t stream);
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream);
+int launch_collide_motions(const mst_mesh* robot, const mst_mesh* env, const double* a, const double* b,
+                           long long M, int steps, uint8_t* invalid, cudaStream_t stream);
 int launch_formation(const double* rb, int F, int m, int pose_dim, const double* off, int D, int K,
                      double* wp, cudaStream_t stream);
 
@@ -199,6 +201,14 @@ extern "C" int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double*
   if (P == 0) return MST_OK;
   if (!pose || !hit) return MST_ERR_INVALID;
   return launch_collide(robot, env, pose, P, pose_dim, hit, (cudaStream_t)stream);
+}
+
+extern "C" int mst_collide_motions(mst_mesh_t robot, mst_mesh_t env, const double* state_a, const double* state_b,
+                                   int M, int steps, uint8_t* invalid, void* stream) {
+  if (!robot || !env || M < 0 || steps < 1) return MST_ERR_INVALID;
+  if (M == 0) return MST_OK;
+  if (!state_a || !state_b || !invalid) return MST_ERR_INVALID;
+  return launch_collide_motions(robot, env, state_a, state_b, M, steps, invalid, (cudaStream_t)stream);
 }
 
 extern "C" int mst_collide_trajectories(const double* coef, const double* dur, int B, int n, int K, int S,

@@ -67,6 +67,79 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
     ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
+// Motion validation for a sampling planner: states (x, y, z, yaw) interpolated linearly between
+// a[m] and b[m] at fractions j/steps, j = 1..steps (the end state included, the start state
+// assumed valid — the discrete motion validation OMPL runs at the resolution set in
+// RB_planning_sep_coll_check.py:79), every interpolated state collision-checked like
+// isStateValid does (:208-215).  invalid[m] = 1 iff some state collides.  invalid[] must be
+// zeroed by the caller (the launcher does it).
+__global__ void __launch_bounds__(128, 4)
+collide_motions_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
+                       const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
+                       const double* __restrict__ sa, const double* __restrict__ sb, long long M, int steps,
+                       uint8_t* __restrict__ invalid) {
+  constexpr int POSE = 1, NP = PoseDim<POSE>::N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ PoseRing<NP> rings[4];
+  PoseRing<NP>& ring = rings[threadIdx.x >> 5];
+  stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
+  const MeshView rb = mesh_view(smem_raw, rl);
+  const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
+  const bool engine = collide_engine_supports(rb, ev);
+  const double* nv = nullptr;
+  unsigned ring_head = 0u, ring_tail = 0u;
+  auto report = [&](int hi32, int lo32, bool h) {
+    if (h) invalid[((long long)hi32 << 32) | (unsigned)lo32] = 1;
+  };
+  const long long total = M * steps;
+  for (long long base = blockIdx.x * (long long)blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    const long long idx = base + threadIdx.x;
+    const bool active = idx < total;
+    const long long m = (active ? idx : total - 1) / steps;
+    const int j = (int)((active ? idx : total - 1) - m * steps) + 1;
+    const double f = (double)j / (double)steps;
+    const double* a = sa + 4 * m;
+    const double* b = sb + 4 * m;
+    double pp[NP];
+    pp[0] = a[0] + (b[0] - a[0]) * f;
+    pp[1] = a[1] + (b[1] - a[1]) * f;
+    pp[2] = a[2] + (b[2] - a[2]) * f;
+    const double yaw = a[3] + (b[3] - a[3]) * f;
+    sincos(yaw * 0.5, &pp[3], &pp[4]);
+    if (!engine) {
+      double R[9];
+      pose_rotation<POSE>(pp, R);
+      if (active && robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true)) invalid[m] = 1;
+      continue;
+    }
+    const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
+    ring_push<POSE>(ring, ring_tail, near, pp, (int)(m >> 32), (int)(m & 0xffffffffll), -1, 0u);
+    while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
+  }
+  while (ring_tail != ring_head)
+    ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
+}
+
+int launch_collide_motions(const mst_mesh* robot, const mst_mesh* env, const double* a, const double* b,
+                           long long M, int steps, uint8_t* invalid, cudaStream_t stream) {
+  if (M == 0) return MST_OK;
+  cudaError_t e = cudaMemsetAsync(invalid, 0, (size_t)M, stream);
+  if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  const size_t smem = robot->layout.bytes + env->layout.bytes;
+  {
+    const int rc = allow_dynamic_smem((const void*)collide_motions_kernel, smem);
+    if (rc != MST_OK) return rc;
+  }
+  long long blocks = (M * steps + 127) / 128;
+  const long long cap = (long long)MST_SM_COUNT * 4;
+  if (blocks > cap) blocks = cap;
+  collide_motions_kernel<<<(unsigned)blocks, 128, smem, stream>>>(robot->d_image, robot->layout, robot->bounds,
+                                                                  env->d_image, env->layout, env->bounds, a, b, M,
+                                                                  steps, invalid);
+  return check_launch();
+}
+
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;

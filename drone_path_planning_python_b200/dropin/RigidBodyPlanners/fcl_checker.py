@@ -97,3 +97,11 @@ class Fcl_checker():
         """``poses[P, 4]`` (x, y, z, yaw — ``isStateValid``'s state) or ``[P, 7]``
         (x, y, z, qx, qy, qz, qw) -> uint8 numpy array of collision flags, one launch."""
         return _mst.collide_poses(self.robot.m, self.env.m, np.asarray(poses, dtype=np.float64)).cpu().numpy()
+
+    def check_motions(self, states_a, states_b, steps):
+        """Batched motion validation: ``states_a[M, 4]`` -> ``states_b[M, 4]`` (x, y, z, yaw), each
+        checked at ``steps`` linearly interpolated states (end state included).  Returns a bool
+        numpy array, True where the motion is collision-free."""
+        bad = _mst.collide_motions(self.robot.m, self.env.m, np.asarray(states_a, dtype=np.float64),
+                                   np.asarray(states_b, dtype=np.float64), steps)
+        return ~bad.cpu().numpy().astype(bool)

@@ -201,6 +201,17 @@ int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double* pose, int 
                       int pose_dim, uint8_t* hit, void* stream);
 
 /*
+ * Batched motion validation for the sampling planner: M candidate motions
+ * between states (x, y, z, yaw); each is checked at `steps` states interpolated linearly at
+ * fractions j/steps, j = 1..steps (end state included, start state assumed valid) — what OMPL's
+ * discrete motion validator does one isStateValid callback at a time at the resolution set in
+ * src/RigidBodyPlanners/RB_planning_sep_coll_check.py:79.
+ *   state_a, state_b [M][4]  ->  invalid [M]  (1 iff some interpolated state collides)
+ */
+int mst_collide_motions(mst_mesh_t robot, mst_mesh_t env, const double* state_a, const double* state_b,
+                        int M, int steps, uint8_t* invalid, void* stream);
+
+/*
  * Collision-check already solved trajectories (the second kernel of the pipeline on its own):
  * sample S uniform times per trajectory, robot mesh at each sampled position (yaw = 4th axis
  * when K = 4, else 0), flags as in mst_pipeline.  K must be 3 or 4.

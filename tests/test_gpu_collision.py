@@ -179,3 +179,23 @@ def test_pipeline_answers_every_sample():
         assert int((res.hit > 1).sum()) == 0 and int((res.any_hit > 1).sum()) == 0
         assert torch.equal(res.hit, hit) and torch.equal(res.any_hit, any_hit)
         assert torch.equal(res.any_hit, res.hit.amax(dim=1))
+
+
+def test_batched_motion_validation():
+    """mst_collide_motions == checking every interpolated state separately."""
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(17)
+    robot_tris, env_tris = _soup("custom_triangle_robot"), _soup("env-scene-ltu-experiment")
+    robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
+    M, steps = 5000, 37
+    a = _random_poses(rng, M, 4)
+    b = a + rng.normal(0, 0.4, (M, 4))
+    invalid = mst.collide_motions(robot, env, a, b, steps).cpu().numpy()
+    f = (np.arange(1, steps + 1) / steps)[None, :, None]
+    states = a[:, None, :] + (b - a)[:, None, :] * f
+    each = mst.collide_poses(robot, env, states.reshape(-1, 4)).cpu().numpy().reshape(M, steps)
+    assert np.array_equal(invalid, each.max(axis=1))
+    assert 0.05 < invalid.mean() < 0.95
+    # the planner's own straight line start -> goal crosses the wall (scripts/rigidBodyPath.py:146-147)
+    assert mst.collide_motions(robot, env, [[0, 3, 1, 0]], [[0, 5, 1, 0]], 2000).cpu().numpy().tolist() == [1]
+    assert mst.collide_motions(robot, env, [[0, 3, 1, 0]], [[1, 3.2, 1.2, 0.5]], 2000).cpu().numpy().tolist() == [0]
