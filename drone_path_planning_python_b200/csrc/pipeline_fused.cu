@@ -74,6 +74,24 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   for (int tile = blockIdx.x * FUSED_WARPS + warp; tile < tiles; tile += gridDim.x * FUSED_WARPS) {
     const int b0 = tile * FUSED_WT;
     const int nb = min(FUSED_WT, B - b0);
+    {
+      // pull the NEXT tile's coefficients and durations into L2 while this tile is processed:
+      // the batch is far larger than L2, so they come from HBM, and the first Horner step of a
+      // new piece was the top stall of the kernel (15 % of warp-stall samples)
+      const long long nt = (long long)tile + (long long)gridDim.x * FUSED_WARPS;
+      if (nt < tiles) {
+        const size_t nb0 = (size_t)nt * FUSED_WT;
+        const int nnb = (int)min((long long)FUSED_WT, (long long)B - (long long)nb0);
+        const char* cbase = reinterpret_cast<const char*>(coef + nb0 * n * K * MST_NCOEF);
+        const size_t cbytes = (size_t)nnb * n * K * MST_NCOEF * sizeof(double);
+        for (size_t off = (size_t)lane * 128; off < cbytes; off += 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + off));
+        const char* dbase = reinterpret_cast<const char*>(dur + nb0 * n);
+        const size_t dbytes = (size_t)nnb * n * sizeof(double);
+        for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
+      }
+    }
     __syncwarp();  // previous tile's tables are no longer read
     if (lane < nb) {
       const double* T = dur + (size_t)(b0 + lane) * n;
