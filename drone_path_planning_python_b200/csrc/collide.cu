@@ -60,7 +60,7 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
     }
     const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
     if (active && !near) hit[idx] = 0;
-    ring_push<POSE>(ring, ring_tail, near, pp, (int)(idx >> 32), (int)(idx & 0xffffffffll), -1, 0u);
+    ring_push<POSE>(ring, ring_tail, near, pp, (int)(idx >> 32), (int)(idx & 0xffffffffll), -1, 0u, 0u);
     while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
   }
   while (ring_tail != ring_head)
@@ -114,7 +114,7 @@ collide_motions_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBo
       continue;
     }
     const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
-    ring_push<POSE>(ring, ring_tail, near, pp, (int)(m >> 32), (int)(m & 0xffffffffll), -1, 0u);
+    ring_push<POSE>(ring, ring_tail, near, pp, (int)(m >> 32), (int)(m & 0xffffffffll), -1, 0u, 0u);
     while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
   }
   while (ring_tail != ring_head)

@@ -6,6 +6,9 @@
 
 #include "mst_common.cuh"
 
+// hides a value's origin from the optimiser (both compilers take the empty asm)
+#define MST_OPAQUE(x) asm volatile("" : "+r"(x))
+
 namespace mst {
 
 struct V3 { double x, y, z; };
@@ -61,22 +64,22 @@ __host__ __device__ inline bool triangles_intersect(V3 P1, V3 P2, V3 P3, V3 Q1, 
 // comparison).  Parallel / coplanar / degenerate pairs (plane normals not independent) go
 // to the 17-axis test, which is what decides them in FCL too.  The two predicates can only
 // disagree inside the rounding band around touching configurations.
+// Written with selects instead of one assignment block per case: the compiler turned the
+// case blocks (and the dominant-axis choice below) into separate code paths, which a warp
+// whose lanes hold different triangle pairs then walked one after the other with a third
+// of its lanes each (profiles/r1_collision_history.md, generation r1g).
 __host__ __device__ __forceinline__ bool interval_terms(double v0, double v1, double v2, double d0, double d1,
                                                         double d2, double& a, double& b, double& c, double& x0,
                                                         double& x1) {
-  if (d0 * d1 > 0.0) {            // v2 alone on its side (or on the plane)
-    a = v2; b = (v0 - v2) * d2; c = (v1 - v2) * d2; x0 = d2 - d0; x1 = d2 - d1;
-  } else if (d0 * d2 > 0.0) {     // v1 alone
-    a = v1; b = (v0 - v1) * d1; c = (v2 - v1) * d1; x0 = d1 - d0; x1 = d1 - d2;
-  } else if (d1 * d2 > 0.0 || d0 != 0.0) {  // v0 alone
-    a = v0; b = (v1 - v0) * d0; c = (v2 - v0) * d0; x0 = d0 - d1; x1 = d0 - d2;
-  } else if (d1 != 0.0) {
-    a = v1; b = (v0 - v1) * d1; c = (v2 - v1) * d1; x0 = d1 - d0; x1 = d1 - d2;
-  } else if (d2 != 0.0) {
-    a = v2; b = (v0 - v2) * d2; c = (v1 - v2) * d2; x0 = d2 - d0; x1 = d2 - d1;
-  } else {
-    return false;                 // the triangle lies in the other plane
-  }
+  // the vertex that is alone on its side of the other plane (or the one off the plane)
+  const bool s01 = d0 * d1 > 0.0, s02 = d0 * d2 > 0.0, s12 = d1 * d2 > 0.0;
+  int lone = s01 ? 2 : (s02 ? 1 : ((s12 || d0 != 0.0) ? 0 : (d1 != 0.0 ? 1 : (d2 != 0.0 ? 2 : -1))));
+  MST_OPAQUE(lone);               // or the cases are threaded into separate copies of what follows
+  if (lone < 0) return false;     // the triangle lies in the other plane
+  const double va = lone == 0 ? v0 : (lone == 1 ? v1 : v2), da = lone == 0 ? d0 : (lone == 1 ? d1 : d2);
+  const double vb = lone == 0 ? v1 : v0, db = lone == 0 ? d1 : d0;
+  const double vc = lone == 2 ? v1 : v2, dc = lone == 2 ? d1 : d2;
+  a = va; b = (vb - va) * da; c = (vc - va) * da; x0 = da - db; x1 = da - dc;
   return true;
 }
 
@@ -97,10 +100,14 @@ __host__ __device__ inline bool triangles_intersect_interval(V3 P1, V3 P2, V3 P3
   // normals (numerically) dependent: parallel planes, coplanar or degenerate triangles
   const double scale = (fabs(n1.x) + fabs(n1.y) + fabs(n1.z)) * (fabs(n2.x) + fabs(n2.y) + fabs(n2.z));
   if (!(dmax > 1e-12 * scale)) return triangles_intersect(P1, P2, P3, Q1, Q2, Q3);
-  double pv1, pv2, pv3, qv1, qv2, qv3;  // coordinate along the dominant axis of the line
-  if (ax >= ay && ax >= az) { pv1 = 0.0; pv2 = p2.x; pv3 = p3.x; qv1 = q1.x; qv2 = q2.x; qv3 = q3.x; }
-  else if (ay >= az)        { pv1 = 0.0; pv2 = p2.y; pv3 = p3.y; qv1 = q1.y; qv2 = q2.y; qv3 = q3.y; }
-  else                      { pv1 = 0.0; pv2 = p2.z; pv3 = p3.z; qv1 = q1.z; qv2 = q2.z; qv3 = q3.z; }
+  // coordinate along the dominant axis of the line (selects, see interval_terms)
+  int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+  MST_OPAQUE(axis);
+  const bool ux = axis == 0, uy = axis == 1;
+  const double pv1 = 0.0;
+  const double pv2 = ux ? p2.x : (uy ? p2.y : p2.z), pv3 = ux ? p3.x : (uy ? p3.y : p3.z);
+  const double qv1 = ux ? q1.x : (uy ? q1.y : q1.z), qv2 = ux ? q2.x : (uy ? q2.y : q2.z);
+  const double qv3 = ux ? q3.x : (uy ? q3.y : q3.z);
   double a, b, c, x0, x1, d, e, f, y0, y1;
   if (!interval_terms(pv1, pv2, pv3, dp1, dp2, dp3, a, b, c, x0, x1) ||
       !interval_terms(qv1, qv2, qv3, dq1, dq2, dq3, d, e, f, y0, y1))
@@ -346,12 +353,13 @@ struct PoseRing {
   int id0[COLLIDE_RING], id1[COLLIDE_RING];  // caller's identification of the pose
   int e[COLLIDE_RING];                       // cursor: env triangle whose `need` bits are current (-1: none yet)
   unsigned need[COLLIDE_RING];               // cursor: robot triangles still to test against triangle e
+  unsigned emask[COLLIDE_RING];              // cursor: triangles after e in e's block of 32 whose box the robot's meets
 };
 
 // append the poses of the lanes with `push` set (ballot-compacted); all 32 lanes call it
 template <int POSE>
 __device__ __forceinline__ void ring_push(PoseRing<PoseDim<POSE>::N>& ring, unsigned& tail, bool push, const double* pp,
-                                          int id0, int id1, int e, unsigned need) {
+                                          int id0, int id1, int e, unsigned need, unsigned emask) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   __syncwarp();
@@ -362,6 +370,7 @@ __device__ __forceinline__ void ring_push(PoseRing<PoseDim<POSE>::N>& ring, unsi
 #pragma unroll
     for (int i = 0; i < PoseDim<POSE>::N; ++i) ring.pose[slot][i] = pp[i];
     ring.id0[slot] = id0; ring.id1[slot] = id1; ring.e[slot] = e; ring.need[slot] = need;
+    ring.emask[slot] = emask;
   }
   tail += __popc(vote);
   __syncwarp();
@@ -382,14 +391,13 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
   for (int i = 0; i < NP; ++i) pp[i] = ring.pose[slot][i];
   const int id0 = ring.id0[slot], id1 = ring.id1[slot];
   int e = ring.e[slot];
-  unsigned need = ring.need[slot];
+  unsigned need = ring.need[slot], emask = ring.emask[slot];
   __syncwarp();  // entries are in registers: the slots may be reused by the re-queue below
   head += (unsigned)count;
 
   double R[9], lo[3], hi[3];
   pose_rotation<POSE>(pp, R);
   robot_world_box<POSE>(pp, R, rbb, lo, hi);
-  const unsigned all = rb.V >= 32 ? ~0u : ((1u << rb.V) - 1u);
   bool hit = false, exhausted = !valid;
 #pragma unroll 1
   for (int round = 0; round < COLLIDE_ROUNDS; ++round) {
@@ -403,42 +411,51 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
       // advanced `tail` differently and ring entries were overwritten (poses never reported;
       // caught by tests/test_gpu_collision.py::test_every_pose_is_answered_once).
       while (need == 0u && !exhausted) {
-        ++e;
-        if (e >= ev.T) {
-          exhausted = true;
+        if (emask == 0u) {
+          // next block of 32 env triangles: all their boxes against the robot's in one pass, so
+          // that the plane tests below run on lanes that each HAVE a box-passing triangle
+          // (walking e one by one, a quarter of the lanes passed the box test at any e)
+          const int base = ((e >> 5) + 1) << 5;
+          if (base >= ev.T) {
+            exhausted = true;
+          } else {
+            const int cnt = min(32, ev.T - base);
+            const double* bx = ev.box + 6 * base;
+            for (int i = 0; i < cnt; ++i, bx += 6)
+              emask |= (unsigned)(!(hi[0] < bx[0] || lo[0] > bx[3] || hi[1] < bx[1] || lo[1] > bx[4] ||
+                                    hi[2] < bx[2] || lo[2] > bx[5])) << i;
+            e = base + 31;  // nothing of this block consumed yet; (e >> 5) names the block
+          }
         } else {
-          const double* bx = ev.box + 6 * e;
-          if (!(hi[0] < bx[0] || lo[0] > bx[3] || hi[1] < bx[1] || lo[1] > bx[4] || hi[2] < bx[2] || lo[2] > bx[5])) {
-            const double* pl = ev.plane + 4 * e;
-            const double off = pl[0] * pp[0] + pl[1] * pp[1] + pl[2] * pp[2] - pl[3];
-            unsigned above = 0u, below = 0u;
-            if (POSE == 0) {
-              const double* row = nv + e * rb.V;
-              for (int v = 0; v < rb.V; ++v) {
-                const double dist = row[v] + off;
-                above |= (unsigned)(dist > 0.0) << v;
-                below |= (unsigned)(dist < 0.0) << v;
-              }
-            } else {
-              // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
-              const double m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
-              const double m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
-              const double m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
-              for (int v = 0; v < rb.V; ++v) {
-                const double* p = rb.vert + 3 * v;
-                const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
-                above |= (unsigned)(dist > 0.0) << v;
-                below |= (unsigned)(dist < 0.0) << v;
-              }
+          e = (e & ~31) | (__ffs(emask) - 1);
+          emask &= emask - 1u;
+          const double* pl = ev.plane + 4 * e;
+          const double off = pl[0] * pp[0] + pl[1] * pp[1] + pl[2] * pp[2] - pl[3];
+          // robot triangles with a corner that is not strictly above / not strictly below the
+          // plane of e; a triangle in both sets straddles or touches the plane
+          unsigned not_above = 0u, not_below = 0u;
+          if (POSE == 0) {
+            const double* row = nv + e * rb.V;
+            for (int v = 0; v < rb.V; ++v) {
+              const double dist = row[v] + off;
+              const unsigned tv = rb.vtri[v];
+              not_above |= dist > 0.0 ? 0u : tv;
+              not_below |= dist < 0.0 ? 0u : tv;
             }
-            // skip when the whole robot is strictly on one side of the plane
-            if (above != all && below != all) {
-              for (int j = 0; j < rb.T; ++j) {
-                const unsigned mk = (unsigned)rb.mask[j];
-                need |= (unsigned)(!((above & mk) == mk || (below & mk) == mk)) << j;
-              }
+          } else {
+            // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
+            const double m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
+            const double m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
+            const double m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
+            for (int v = 0; v < rb.V; ++v) {
+              const double* p = rb.vert + 3 * v;
+              const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
+              const unsigned tv = rb.vtri[v];
+              not_above |= dist > 0.0 ? 0u : tv;
+              not_below |= dist < 0.0 ? 0u : tv;
             }
           }
+          need = not_above & not_below;
         }
       }
       if (!exhausted) {
@@ -465,7 +482,7 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
   // a pose whose last candidate was just consumed and missed may still have later env triangles:
   // it is "exhausted" only when the cursor ran off the end
   if (valid && (hit || exhausted)) report(id0, id1, hit);
-  ring_push<POSE>(ring, tail, valid && !hit && !exhausted, pp, id0, id1, e, need);
+  ring_push<POSE>(ring, tail, valid && !hit && !exhausted, pp, id0, id1, e, need, emask);
 }
 #endif  // __CUDACC__
 

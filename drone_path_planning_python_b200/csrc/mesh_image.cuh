@@ -35,6 +35,9 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
   double* ivert = (double*)(base + layout->off_vert);
   int* iidx = (int*)(base + layout->off_idx);
   unsigned long long* imask = (unsigned long long*)(base + layout->off_mask);
+  unsigned* ivtri = (unsigned*)(base + layout->off_vtri);
+  for (int t = 0; t < T && t < 32; ++t)
+    for (int c = 0; c < 3; ++c) ivtri[idx[3 * t + c]] |= 1u << t;
   memcpy(itri, tri, sizeof(double) * 9 * (size_t)T);
   memcpy(ivert, uv, sizeof(double) * 3 * (size_t)V);
   memcpy(iidx, idx, sizeof(int) * 3 * (size_t)T);

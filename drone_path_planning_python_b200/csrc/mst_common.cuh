@@ -77,12 +77,13 @@ struct MeshView {
   const double* plane;  // nx, ny, nz, d  with n = (Q2-Q1) x (Q3-Q2), d = n . Q1
   const double* vert;   // unique vertices
   const int* idx;       // corner -> unique vertex
-  const unsigned long long* mask;
+  const unsigned long long* mask;  // per triangle: bits of its (first 64) unique vertices
+  const unsigned* vtri;            // per unique vertex: bits of the (first 32) triangles that use it
 };
 
 struct MeshLayout {
   int T, V;
-  size_t off_box, off_plane, off_vert, off_idx, off_mask, bytes;  // byte offsets from base
+  size_t off_box, off_plane, off_vert, off_idx, off_mask, off_vtri, bytes;  // byte offsets from base
 };
 
 __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
@@ -96,6 +97,7 @@ __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
   L.off_idx = o;   o += sizeof(int) * 3 * (size_t)T;
   o = (o + 15) & ~(size_t)15;
   L.off_mask = o;  o += sizeof(unsigned long long) * (size_t)T;
+  L.off_vtri = o;  o += sizeof(unsigned) * (size_t)V;
   L.bytes = (o + 15) & ~(size_t)15;
   return L;
 }
@@ -110,6 +112,7 @@ __host__ __device__ __forceinline__ MeshView mesh_view(const void* base, const M
   v.vert = (const double*)(b + L.off_vert);
   v.idx = (const int*)(b + L.off_idx);
   v.mask = (const unsigned long long*)(b + L.off_mask);
+  v.vtri = (const unsigned*)(b + L.off_vtri);
   return v;
 }
 

@@ -28,6 +28,7 @@ namespace mst {
 
 constexpr int FUSED_THREADS = 128;
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
+constexpr int FUSED_PF = 4;      // trajectories between the L2 prefetch and the sampling front
 constexpr int FUSED_WT_MAX = 32; // trajectories per warp tile (chosen by the launcher, <= 32)
 
 // Every WARP walks its own tiles of FUSED_WT trajectories (no CTA-wide barrier after the
@@ -62,8 +63,16 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
   if (engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
   __syncthreads();
-  double* knots = nv + (engine ? ev.T * rb.V : 0) + warp * FUSED_WT * (n + 2);
+  double* tables = nv + (engine ? ev.T * rb.V : 0);
+  double* knots = tables + warp * FUSED_WT * (n + 2);
   double* dts = knots + FUSED_WT * (n + 1);
+  // thr[WT][4 * nthr4]: first sample index of pieces 1 .. n-1 (INT_MAX padding), so that the piece
+  // of sample s is the number of thresholds <= s — integer compares without the dependent
+  // shared-memory loads of a bisection over the knots (12 % of the stall samples before)
+  const int nthr4 = (n - 1 + 3) >> 2;
+  int4* thr = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(tables + FUSED_WARPS * FUSED_WT * (n + 2)) + 15) &
+                                      ~(uintptr_t)15) + warp * FUSED_WT * nthr4;
+  const int traj_bytes = n * K * MST_NCOEF * (int)sizeof(double);
   unsigned ring_head = 0u, ring_tail = 0u;  // warp-uniform
 
   // zeroed at the start of the trajectory's tile; every writer of any_hit stores 1
@@ -76,24 +85,28 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   for (int tile = blockIdx.x * FUSED_WARPS + warp; tile < tiles; tile += gridDim.x * FUSED_WARPS) {
     const int b0 = tile * FUSED_WT;
     const int nb = min(FUSED_WT, B - b0);
+    // Coefficients are pulled into L2 FUSED_PF trajectories ahead of the one being sampled (see
+    // prefetch_trajectory below); the next tile's durations, which the table set-up of that tile
+    // reads all at once, are pulled here.  The batch is far larger than L2, so all of it comes
+    // from HBM, and the first Horner step of a new piece was the top stall of the kernel.
+    const long long next_tile = (long long)tile + (long long)gridDim.x * FUSED_WARPS;
+    const int next_b0 = next_tile < tiles ? (int)(next_tile * FUSED_WT) : B;
+    const int next_nb = min(FUSED_WT, B - next_b0);
     {
-      // pull the NEXT tile's coefficients and durations into L2 while this tile is processed:
-      // the batch is far larger than L2, so they come from HBM, and the first Horner step of a
-      // new piece was the top stall of the kernel (15 % of warp-stall samples)
-      const long long nt = (long long)tile + (long long)gridDim.x * FUSED_WARPS;
-      if (nt < tiles) {
-        const size_t nb0 = (size_t)nt * FUSED_WT;
-        const int nnb = (int)min((long long)FUSED_WT, (long long)B - (long long)nb0);
-        const char* cbase = reinterpret_cast<const char*>(coef + nb0 * n * K * MST_NCOEF);
-        const size_t cbytes = (size_t)nnb * n * K * MST_NCOEF * sizeof(double);
-        for (size_t off = (size_t)lane * 128; off < cbytes; off += 32 * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + off));
-        const char* dbase = reinterpret_cast<const char*>(dur + nb0 * n);
-        const size_t dbytes = (size_t)nnb * n * sizeof(double);
-        for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
-      }
+      const char* dbase = reinterpret_cast<const char*>(dur + (size_t)next_b0 * n);
+      const size_t dbytes = (size_t)max(next_nb, 0) * n * sizeof(double);
+      for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
     }
+    // q-th trajectory of this warp counted from the start of the tile; runs on into the next tile
+    auto prefetch_trajectory = [&](int q) {
+      const int b = q < nb ? b0 + q : (q - nb < next_nb ? next_b0 + (q - nb) : -1);
+      if (b >= 0) {
+        const char* cbase = reinterpret_cast<const char*>(coef) + (size_t)b * traj_bytes;
+        for (int off = lane * 128; off < traj_bytes; off += 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + off));
+      }
+    };
     __syncwarp();  // previous tile's tables are no longer read
     if (lane < nb) {
       const double* T = dur + (size_t)(b0 + lane) * n;
@@ -105,24 +118,58 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       any_hit[b0 + lane] = 0;
     }
     __syncwarp();
+    {
+      // thresholds: first s with !(s * dt < knot), found from the quotient and corrected with the
+      // very comparison the bisection over the knots would make
+      const int per = 4 * nthr4;
+      int* th = reinterpret_cast<int*>(thr);
+      for (int item = lane; item < nb * per; item += 32) {
+        const int q = item / per, i = item - q * per;
+        int first = 0x7fffffff;
+        if (i < n - 1) {
+          const double knot = knots[q * (n + 1) + i + 1], dt = dts[q];
+          first = (int)fmin(fmax(ceil(__ddiv_rn(knot, dt)), 0.0), (double)S);
+          while (first > 0 && !(__dmul_rn((double)(first - 1), dt) < knot)) --first;
+          while (first < S && __dmul_rn((double)first, dt) < knot) ++first;
+        }
+        th[item] = first;
+      }
+    }
+    __syncwarp();
     const int work = nb * S;
     // warp-uniform trip count: every lane stays in the loop (ballots), lanes past the end of
     // the tile are simply inactive
     // (trajectory, sample) of this lane, advanced by 32 samples per iteration without dividing
     int tl = 0, s = lane;
+    int pf_tl = 0, pf_base = 0;  // warp-uniform: trajectory whose first sample is at pf_base
+    if (tile < (int)(gridDim.x * FUSED_WARPS))  // first tile of the warp: nothing was pulled ahead of it
+      for (int q = 0; q < FUSED_PF; ++q) prefetch_trajectory(q);
     for (int base = 0; base < work; base += 32, s += 32) {
       const int idx = base + lane;
       const bool active = idx < work;
+      while (base >= pf_base) { prefetch_trajectory(pf_tl + FUSED_PF); ++pf_tl; pf_base += S; }
       while (s >= S) { s -= S; ++tl; }
       if (!active) { tl = nb - 1; s = S - 1; }  // parked on the tile's last sample (not reported)
       const double* kn = knots + tl * (n + 1);
       const double t = __dmul_rn((double)s, dts[tl]);
       // PiecewisePolynomial.eval: first piece with t < acc + T_i, else the last one at
-      // t - sum(T[:-1]); the running sums are non-decreasing, so bisection finds the same piece
-      int piece = 0, last = n - 1;
-      while (piece < last) {
-        const int mid = (piece + last) >> 1;
-        if (t < kn[mid + 1]) last = mid; else piece = mid + 1;
+      // t - sum(T[:-1]); t is non-decreasing in s, so that piece is the number of thresholds <= s
+      int piece = 0;
+      {
+        const int4* th = thr + tl * nthr4;
+        if (nthr4 <= 4) {
+          for (int w = 0; w < nthr4; ++w) {
+            const int4 v = th[w];
+            piece += (int)(s >= v.x) + (int)(s >= v.y) + (int)(s >= v.z) + (int)(s >= v.w);
+          }
+        } else {
+          const int* ti = reinterpret_cast<const int*>(th);
+          int last = n - 1;
+          while (piece < last) {
+            const int mid = (piece + last) >> 1;
+            if (s < ti[mid]) last = mid; else piece = mid + 1;
+          }
+        }
       }
       const double local = __dsub_rn(t, kn[piece]);
       const double* cp = coef + (((size_t)(b0 + tl) * n + piece) * K) * MST_NCOEF;
@@ -152,7 +199,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       }
       const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
       if (active && !near) hit[(size_t)b0 * S + idx] = 0;
-      ring_push<POSE>(ring, ring_tail, near, pp, b0 + tl, s, -1, 0u);
+      ring_push<POSE>(ring, ring_tail, near, pp, b0 + tl, s, -1, 0u, 0u);
       while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
     }
   }
@@ -170,9 +217,11 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
   static const int wt_env = getenv("MST_FUSED_WT") ? atoi(getenv("MST_FUSED_WT")) : 0;
   int FUSED_WT = wt_env > 0 ? wt_env : 16;
   if (FUSED_WT > FUSED_WT_MAX) FUSED_WT = FUSED_WT_MAX;
-  while (FUSED_WT > 1 && sizeof(double) * FUSED_WARPS * FUSED_WT * (size_t)(n + 2) > 24 * 1024) FUSED_WT /= 2;
-  const size_t smem = robot->layout.bytes + env->layout.bytes +
-                      sizeof(double) * ((size_t)env->T * robot->V + FUSED_WARPS * FUSED_WT * (size_t)(n + 2));
+  // per trajectory: knots[n+1], dt, thresholds (4 * ceil((n-1)/4) ints)
+  const size_t per_traj = sizeof(double) * (size_t)(n + 2) + sizeof(int) * 4 * (size_t)((n - 1 + 3) / 4);
+  while (FUSED_WT > 1 && FUSED_WARPS * FUSED_WT * per_traj > 24 * 1024) FUSED_WT /= 2;
+  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * (size_t)env->T * robot->V +
+                      FUSED_WARPS * FUSED_WT * per_traj + 16;
   auto kern = K == 3 ? sample_collide_kernel<3> : sample_collide_kernel<4>;
   {
     const int rc = allow_dynamic_smem((const void*)kern, smem);
