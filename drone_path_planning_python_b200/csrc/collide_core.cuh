@@ -398,6 +398,8 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
   double R[9], lo[3], hi[3];
   pose_rotation<POSE>(pp, R);
   robot_world_box<POSE>(pp, R, rbb, lo, hi);
+  const float flo0 = __double2float_rd(lo[0]), flo1 = __double2float_rd(lo[1]), flo2 = __double2float_rd(lo[2]);
+  const float fhi0 = __double2float_ru(hi[0]), fhi1 = __double2float_ru(hi[1]), fhi2 = __double2float_ru(hi[2]);
   bool hit = false, exhausted = !valid;
 #pragma unroll 1
   for (int round = 0; round < COLLIDE_ROUNDS; ++round) {
@@ -419,11 +421,16 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
           if (base >= ev.T) {
             exhausted = true;
           } else {
+            // single precision with every bound rounded outward: a box pair that meets in double
+            // precision meets here too (the plane and pair tests that follow are the exact ones)
             const int cnt = min(32, ev.T - base);
-            const double* bx = ev.box + 6 * base;
-            for (int i = 0; i < cnt; ++i, bx += 6)
-              emask |= (unsigned)(!(hi[0] < bx[0] || lo[0] > bx[3] || hi[1] < bx[1] || lo[1] > bx[4] ||
-                                    hi[2] < bx[2] || lo[2] > bx[5])) << i;
+            const float4* fb = reinterpret_cast<const float4*>(ev.fbox) + 2 * base;
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+              const float4 b0 = fb[2 * i], b1 = fb[2 * i + 1];  // min x y z, max x | max y z, pad
+              emask |= (unsigned)(!(fhi0 < b0.x || flo0 > b0.w || fhi1 < b0.y || flo1 > b1.x || fhi2 < b0.z ||
+                                    flo2 > b1.y)) << i;
+            }
             e = base + 31;  // nothing of this block consumed yet; (e >> 5) names the block
           }
         } else {

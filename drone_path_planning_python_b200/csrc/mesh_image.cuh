@@ -36,6 +36,7 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
   int* iidx = (int*)(base + layout->off_idx);
   unsigned long long* imask = (unsigned long long*)(base + layout->off_mask);
   unsigned* ivtri = (unsigned*)(base + layout->off_vtri);
+  float* ifbox = (float*)(base + layout->off_fbox);
   for (int t = 0; t < T && t < 32; ++t)
     for (int c = 0; c < 3; ++c) ivtri[idx[3 * t + c]] |= 1u << t;
   memcpy(itri, tri, sizeof(double) * 9 * (size_t)T);
@@ -61,6 +62,13 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
       if (idx[3 * t + c] < 64) mk |= 1ull << idx[3 * t + c];
     }
     imask[t] = mk;
+    for (int k = 0; k < 3; ++k) {
+      float lo = (float)box[k], hi = (float)box[3 + k];
+      if ((double)lo > box[k]) lo = nextafterf(lo, -INFINITY);
+      if ((double)hi < box[3 + k]) hi = nextafterf(hi, INFINITY);
+      ifbox[8 * t + k] = lo;
+      ifbox[8 * t + 3 + k] = hi;
+    }
     for (int k = 0; k < 3; ++k) {
       if (box[k] < bounds->root[k]) bounds->root[k] = box[k];
       if (box[3 + k] > bounds->root[3 + k]) bounds->root[3 + k] = box[3 + k];

@@ -79,11 +79,12 @@ struct MeshView {
   const int* idx;       // corner -> unique vertex
   const unsigned long long* mask;  // per triangle: bits of its (first 64) unique vertices
   const unsigned* vtri;            // per unique vertex: bits of the (first 32) triangles that use it
+  const float* fbox;               // per triangle, 8 floats: the AABB rounded OUTWARD (min xyz, max xyz, 2 pad)
 };
 
 struct MeshLayout {
   int T, V;
-  size_t off_box, off_plane, off_vert, off_idx, off_mask, off_vtri, bytes;  // byte offsets from base
+  size_t off_box, off_plane, off_vert, off_idx, off_mask, off_vtri, off_fbox, bytes;  // byte offsets from base
 };
 
 __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
@@ -98,6 +99,8 @@ __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
   o = (o + 15) & ~(size_t)15;
   L.off_mask = o;  o += sizeof(unsigned long long) * (size_t)T;
   L.off_vtri = o;  o += sizeof(unsigned) * (size_t)V;
+  o = (o + 15) & ~(size_t)15;
+  L.off_fbox = o;  o += sizeof(float) * 8 * (size_t)T;
   L.bytes = (o + 15) & ~(size_t)15;
   return L;
 }
@@ -113,6 +116,7 @@ __host__ __device__ __forceinline__ MeshView mesh_view(const void* base, const M
   v.idx = (const int*)(b + L.off_idx);
   v.mask = (const unsigned long long*)(b + L.off_mask);
   v.vtri = (const unsigned*)(b + L.off_vtri);
+  v.fbox = (const float*)(b + L.off_fbox);
   return v;
 }
 

@@ -41,7 +41,7 @@ constexpr int FUSED_WT_MAX = 32; // trajectories per warp tile (chosen by the la
 // appended (ballot-compacted) to the warp's pose ring, and only when 32 of them are waiting
 // does the warp run the collision engine (collide_core.cuh) — on a DENSE batch, whatever mix
 // of near and far samples the trajectories produce.
-template <int K>
+template <int K, bool TAB>
 __global__ void __launch_bounds__(FUSED_THREADS, 4)
 sample_collide_kernel(const double* __restrict__ coef, const double* __restrict__ dur, int B, int n, int S, int FUSED_WT,
                       const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
@@ -66,12 +66,13 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   double* tables = nv + (engine ? ev.T * rb.V : 0);
   double* knots = tables + warp * FUSED_WT * (n + 2);
   double* dts = knots + FUSED_WT * (n + 1);
-  // thr[WT][4 * nthr4]: first sample index of pieces 1 .. n-1 (INT_MAX padding), so that the piece
-  // of sample s is the number of thresholds <= s — integer compares without the dependent
-  // shared-memory loads of a bisection over the knots (12 % of the stall samples before)
-  const int nthr4 = (n - 1 + 3) >> 2;
-  int4* thr = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(tables + FUSED_WARPS * FUSED_WT * (n + 2)) + 15) &
-                                      ~(uintptr_t)15) + warp * FUSED_WT * nthr4;
+  // thr[WT][n]: first sample index of pieces 1 .. n-1, and (when the launcher found room: TAB)
+  // piece_of[WT][S]: the piece of every sample as a byte, filled range by range from thr — the
+  // per-sample search for the piece (a bisection over the knots with dependent shared-memory
+  // loads, 12 % of the stall samples) becomes one byte load
+  int* thr = reinterpret_cast<int*>(tables + FUSED_WARPS * FUSED_WT * (n + 2)) + warp * FUSED_WT * n;
+  uint8_t* piece_of = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(tables + FUSED_WARPS * FUSED_WT * (n + 2)) +
+                                                 FUSED_WARPS * FUSED_WT * n) + warp * FUSED_WT * S;
   const int traj_bytes = n * K * MST_NCOEF * (int)sizeof(double);
   unsigned ring_head = 0u, ring_tail = 0u;  // warp-uniform
 
@@ -118,24 +119,28 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       any_hit[b0 + lane] = 0;
     }
     __syncwarp();
-    {
-      // thresholds: first s with !(s * dt < knot), found from the quotient and corrected with the
-      // very comparison the bisection over the knots would make
-      const int per = 4 * nthr4;
-      int* th = reinterpret_cast<int*>(thr);
-      for (int item = lane; item < nb * per; item += 32) {
-        const int q = item / per, i = item - q * per;
-        int first = 0x7fffffff;
-        if (i < n - 1) {
-          const double knot = knots[q * (n + 1) + i + 1], dt = dts[q];
-          first = (int)fmin(fmax(ceil(__ddiv_rn(knot, dt)), 0.0), (double)S);
-          while (first > 0 && !(__dmul_rn((double)(first - 1), dt) < knot)) --first;
-          while (first < S && __dmul_rn((double)first, dt) < knot) ++first;
-        }
-        th[item] = first;
+    // thresholds: first s with !(s * dt < knot), found from the quotient and corrected with the
+    // very comparison PiecewisePolynomial.eval makes (t is non-decreasing in s)
+    for (int item = lane; item < nb * n; item += 32) {
+      const int q = item / n, i = item - q * n;
+      int first = S;
+      if (i < n - 1) {
+        const double knot = knots[q * (n + 1) + i + 1], dt = dts[q];
+        first = (int)fmin(fmax(ceil(__ddiv_rn(knot, dt)), 0.0), (double)S);
+        while (first > 0 && !(__dmul_rn((double)(first - 1), dt) < knot)) --first;
+        while (first < S && __dmul_rn((double)first, dt) < knot) ++first;
       }
+      thr[item] = first;  // thr[q][n-1] = S closes the last piece
     }
     __syncwarp();
+    if (TAB) {
+      for (int item = lane; item < nb * n; item += 32) {
+        const int q = item / n, i = item - q * n;
+        const int from = i ? thr[item - 1] : 0, to = thr[item];
+        for (int x = from; x < to; ++x) piece_of[q * S + x] = (uint8_t)i;
+      }
+      __syncwarp();
+    }
     const int work = nb * S;
     // warp-uniform trip count: every lane stays in the loop (ballots), lanes past the end of
     // the tile are simply inactive
@@ -153,22 +158,17 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       const double* kn = knots + tl * (n + 1);
       const double t = __dmul_rn((double)s, dts[tl]);
       // PiecewisePolynomial.eval: first piece with t < acc + T_i, else the last one at
-      // t - sum(T[:-1]); t is non-decreasing in s, so that piece is the number of thresholds <= s
+      // t - sum(T[:-1]) = the number of thresholds <= s.  (Decreasing stamps — reported in info —
+      // can leave table entries unwritten: the clamp keeps the coefficient read inside the batch.)
       int piece = 0;
-      {
-        const int4* th = thr + tl * nthr4;
-        if (nthr4 <= 4) {
-          for (int w = 0; w < nthr4; ++w) {
-            const int4 v = th[w];
-            piece += (int)(s >= v.x) + (int)(s >= v.y) + (int)(s >= v.z) + (int)(s >= v.w);
-          }
-        } else {
-          const int* ti = reinterpret_cast<const int*>(th);
-          int last = n - 1;
-          while (piece < last) {
-            const int mid = (piece + last) >> 1;
-            if (s < ti[mid]) last = mid; else piece = mid + 1;
-          }
+      if (TAB) {
+        piece = min((int)piece_of[tl * S + s], n - 1);
+      } else {
+        const int* ti = thr + tl * n;
+        int last = n - 1;
+        while (piece < last) {
+          const int mid = (piece + last) >> 1;
+          if (s < ti[mid]) last = mid; else piece = mid + 1;
         }
       }
       const double local = __dsub_rn(t, kn[piece]);
@@ -217,12 +217,15 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
   static const int wt_env = getenv("MST_FUSED_WT") ? atoi(getenv("MST_FUSED_WT")) : 0;
   int FUSED_WT = wt_env > 0 ? wt_env : 16;
   if (FUSED_WT > FUSED_WT_MAX) FUSED_WT = FUSED_WT_MAX;
-  // per trajectory: knots[n+1], dt, thresholds (4 * ceil((n-1)/4) ints)
-  const size_t per_traj = sizeof(double) * (size_t)(n + 2) + sizeof(int) * 4 * (size_t)((n - 1 + 3) / 4);
+  // per trajectory: knots[n+1], dt, thresholds[n], and the piece-of-sample bytes when they are
+  // small next to the rest
+  const bool tab = n <= 255 && S <= 1024;
+  const size_t per_traj = sizeof(double) * (size_t)(n + 2) + sizeof(int) * (size_t)n + (tab ? (size_t)S : 0);
   while (FUSED_WT > 1 && FUSED_WARPS * FUSED_WT * per_traj > 24 * 1024) FUSED_WT /= 2;
   const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * (size_t)env->T * robot->V +
-                      FUSED_WARPS * FUSED_WT * per_traj + 16;
-  auto kern = K == 3 ? sample_collide_kernel<3> : sample_collide_kernel<4>;
+                      FUSED_WARPS * FUSED_WT * per_traj;
+  auto kern = K == 3 ? (tab ? sample_collide_kernel<3, true> : sample_collide_kernel<3, false>)
+                     : (tab ? sample_collide_kernel<4, true> : sample_collide_kernel<4, false>);
   {
     const int rc = allow_dynamic_smem((const void*)kern, smem);
     if (rc != MST_OK) return rc;
