@@ -96,6 +96,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     {
       const char* dbase = reinterpret_cast<const char*>(dur + (size_t)next_b0 * n);
       const size_t dbytes = (size_t)max(next_nb, 0) * n * sizeof(double);
+#pragma unroll 1
       for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
     }
@@ -104,6 +105,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       const int b = q < nb ? b0 + q : (q - nb < next_nb ? next_b0 + (q - nb) : -1);
       if (b >= 0) {
         const char* cbase = reinterpret_cast<const char*>(coef) + (size_t)b * traj_bytes;
+#pragma unroll 1
         for (int off = lane * 128; off < traj_bytes; off += 32 * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + off));
       }
@@ -114,6 +116,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       double* kn = knots + lane * (n + 1);
       double acc = 0.0;
       kn[0] = 0.0;
+#pragma unroll 1
       for (int i = 0; i < n; ++i) { acc = __dadd_rn(acc, T[i]); kn[i + 1] = acc; }
       dts[lane] = __ddiv_rn(acc, (double)S);
       any_hit[b0 + lane] = 0;
@@ -121,6 +124,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     __syncwarp();
     // thresholds: first s with !(s * dt < knot), found from the quotient and corrected with the
     // very comparison PiecewisePolynomial.eval makes (t is non-decreasing in s)
+#pragma unroll 1
     for (int item = lane; item < nb * n; item += 32) {
       const int q = item / n, i = item - q * n;
       int first = S;
@@ -134,9 +138,11 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     }
     __syncwarp();
     if (TAB) {
+#pragma unroll 1
       for (int item = lane; item < nb * n; item += 32) {
         const int q = item / n, i = item - q * n;
         const int from = i ? thr[item - 1] : 0, to = thr[item];
+#pragma unroll 1
         for (int x = from; x < to; ++x) piece_of[q * S + x] = (uint8_t)i;
       }
       __syncwarp();
@@ -148,6 +154,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     int tl = 0, s = lane;
     int pf_tl = 0, pf_base = 0;  // warp-uniform: trajectory whose first sample is at pf_base
     if (tile < (int)(gridDim.x * FUSED_WARPS))  // first tile of the warp: nothing was pulled ahead of it
+#pragma unroll 1
       for (int q = 0; q < FUSED_PF; ++q) prefetch_trajectory(q);
     for (int base = 0; base < work; base += 32, s += 32) {
       const int idx = base + lane;
