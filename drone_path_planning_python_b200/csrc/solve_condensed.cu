@@ -131,6 +131,8 @@ condensed_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
 // trajectory write adjacent 64-byte coefficient rows and read adjacent waypoint values.
 // Inputs of the warp's groups are one contiguous range each: copied into shared memory with
 // coalesced loads before use.
+constexpr int COLS_TREGS = 4, COLS_WREGS = 12;  // register tile of the input pipeline, doubles per lane
+
 template <int dummy>
 __global__ void __launch_bounds__(128)
 condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps, int groups, int n,
@@ -155,13 +157,40 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   const long long sets = ((long long)groups + GPW - 1) / GPW;
+  // Software pipeline of the input copies: the NEXT set's stamps and waypoints are loaded into
+  // registers before this set is solved and stored to shared memory afterwards, so their
+  // latency (23 % of the kernel's stall samples when the copy was synchronous) is covered by
+  // the solve.  Used when a set's inputs fit the register tile.
+  const bool piped = GPW * (n + 1) <= 32 * COLS_TREGS && GPW * (n + 1) * R <= 32 * COLS_WREGS;
+  double tr[COLS_TREGS], wr[COLS_WREGS];
+  auto load_set = [&](long long set2) {
+    if (set2 >= sets) return;
+    const long long h0 = set2 * GPW;
+    const int c2 = (int)min((long long)GPW, groups - h0);
+    const double* tb = tstamps + (size_t)h0 * (n + 1);
+    const double* wb = wp + (size_t)h0 * (n + 1) * R;
+#pragma unroll
+    for (int j = 0; j < COLS_TREGS; ++j) if (lane + 32 * j < c2 * (n + 1)) tr[j] = __ldg(tb + lane + 32 * j);
+#pragma unroll
+    for (int j = 0; j < COLS_WREGS; ++j) if (lane + 32 * j < c2 * (n + 1) * R) wr[j] = __ldg(wb + lane + 32 * j);
+  };
+  if (piped) load_set(blockIdx.x * (long long)warps + warp);
   for (long long set = blockIdx.x * (long long)warps + warp; set < sets; set += (long long)gridDim.x * warps) {
     const long long g0 = set * GPW;
     const int cnt = (int)min((long long)GPW, groups - g0);
     __syncwarp();  // the previous set's tiles are no longer read
-    for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = tstamps[(size_t)g0 * (n + 1) + i];
-    for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[i] = wp[(size_t)g0 * (n + 1) * R + i];
+    if (piped) {
+      // this set's inputs were loaded into registers while the previous set was solved
+#pragma unroll
+      for (int j = 0; j < COLS_TREGS; ++j) if (lane + 32 * j < cnt * (n + 1)) wt[lane + 32 * j] = tr[j];
+#pragma unroll
+      for (int j = 0; j < COLS_WREGS; ++j) if (lane + 32 * j < cnt * (n + 1) * R) ww[lane + 32 * j] = wr[j];
+    } else {
+      for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = tstamps[(size_t)g0 * (n + 1) + i];
+      for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[i] = wp[(size_t)g0 * (n + 1) * R + i];
+    }
     __syncwarp();
+    if (piped) load_set(set + (long long)gridDim.x * warps);
     const bool mine = lane_used && gl < cnt;
     const long long g = g0 + gl;
     const double* tg = wt + (size_t)gl * (n + 1);
