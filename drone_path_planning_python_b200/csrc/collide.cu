@@ -143,7 +143,7 @@ int launch_collide_motions(const mst_mesh* robot, const mst_mesh* env, const dou
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;
-  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * (size_t)env->T * robot->V;
+  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * collide_table_doubles(env->T, robot->V);
   void (*kern)(const void*, MeshLayout, MeshBounds, const void*, MeshLayout, MeshBounds, const double*, long long,
                uint8_t*) = pose_dim == 3 ? collide_kernel<0> : (pose_dim == 4 ? collide_kernel<1> : collide_kernel<2>);
   {

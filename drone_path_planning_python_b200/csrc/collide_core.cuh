@@ -294,11 +294,20 @@ __host__ __device__ __forceinline__ bool collide_engine_supports(const MeshView&
   return rb.V <= COLLIDE_MAX_V && rb.T <= COLLIDE_MAX_TR && ev.T < (1 << 20);
 }
 
-// nv[e * V + v] = n_e . vertex_v ; every thread of the CTA calls it, followed by a CTA barrier
+// Translation-only poses: tables of the env planes against the robot's unique vertices, which a
+// translation leaves constant (the signed distance of a moved vertex is then one add).  Four
+// rows of V per env triangle: nv[(4 e + 0) V + v] = n_e . vertex_v (the triangle's plane),
+// nv[(4 e + 1 + k) V + v] = m_ek . vertex_v (edge plane k).  Every thread of the CTA calls it,
+// followed by a CTA barrier.
+constexpr int COLLIDE_TABLE_ROWS = 4;
+__host__ __device__ __forceinline__ size_t collide_table_doubles(int envT, int robotV) {
+  return (size_t)COLLIDE_TABLE_ROWS * envT * robotV;
+}
 __device__ __forceinline__ void build_plane_vertex_table(const MeshView& rb, const MeshView& ev, double* nv) {
-  for (int i = threadIdx.x; i < ev.T * rb.V; i += blockDim.x) {
-    const int e = i / rb.V, v = i - e * rb.V;
-    const double* pl = ev.plane + 4 * e;
+  for (int i = threadIdx.x; i < COLLIDE_TABLE_ROWS * ev.T * rb.V; i += blockDim.x) {
+    const int row = i / rb.V, v = i - row * rb.V;
+    const int e = row >> 2, j = row & 3;
+    const double* pl = j == 0 ? ev.plane + 4 * e : ev.edge + 12 * e + 4 * (j - 1);
     const double* p = rb.vert + 3 * v;
     nv[i] = pl[0] * p[0] + pl[1] * p[1] + pl[2] * p[2];
   }
@@ -441,30 +450,48 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
           const double* pl = ev.plane + 4 * e;
           const double off = pl[0] * pp[0] + pl[1] * pp[1] + pl[2] * pp[2] - pl[3];
           // robot triangles with a corner that is not strictly above / not strictly below the
-          // plane of e; a triangle in both sets straddles or touches the plane
-          unsigned not_above = 0u, not_below = 0u;
+          // plane of e (a triangle in both sets straddles or touches the plane), and with a
+          // corner that is not beyond edge k of e (a triangle whose corners all are cannot touch
+          // e; without this cull a robot crossing the plane of a face next to e, not inside it,
+          // spent all its triangles on e: 45 % of the pair tests ended that way)
+          unsigned not_above = 0u, not_below = 0u, in0 = 0u, in1 = 0u, in2 = 0u;
+          const double* ed = ev.edge + 12 * e;
+          const double o0 = ed[0] * pp[0] + ed[1] * pp[1] + ed[2] * pp[2] - ed[3];
+          const double o1 = ed[4] * pp[0] + ed[5] * pp[1] + ed[6] * pp[2] - ed[7];
+          const double o2 = ed[8] * pp[0] + ed[9] * pp[1] + ed[10] * pp[2] - ed[11];
           if (POSE == 0) {
-            const double* row = nv + e * rb.V;
+            const double* row = nv + (size_t)e * COLLIDE_TABLE_ROWS * rb.V;
             for (int v = 0; v < rb.V; ++v) {
               const double dist = row[v] + off;
               const unsigned tv = rb.vtri[v];
               not_above |= dist > 0.0 ? 0u : tv;
               not_below |= dist < 0.0 ? 0u : tv;
+              in0 |= row[rb.V + v] + o0 > 0.0 ? 0u : tv;
+              in1 |= row[2 * rb.V + v] + o1 > 0.0 ? 0u : tv;
+              in2 |= row[3 * rb.V + v] + o2 > 0.0 ? 0u : tv;
             }
           } else {
-            // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
-            const double m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
-            const double m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
-            const double m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
+            // planes in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
+            double m[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double* q = j == 0 ? pl : ed + 4 * (j - 1);
+              m[j][0] = R[0] * q[0] + R[3] * q[1] + R[6] * q[2];
+              m[j][1] = R[1] * q[0] + R[4] * q[1] + R[7] * q[2];
+              m[j][2] = R[2] * q[0] + R[5] * q[1] + R[8] * q[2];
+            }
             for (int v = 0; v < rb.V; ++v) {
               const double* p = rb.vert + 3 * v;
-              const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
+              const double dist = m[0][0] * p[0] + m[0][1] * p[1] + m[0][2] * p[2] + off;
               const unsigned tv = rb.vtri[v];
               not_above |= dist > 0.0 ? 0u : tv;
               not_below |= dist < 0.0 ? 0u : tv;
+              in0 |= m[1][0] * p[0] + m[1][1] * p[1] + m[1][2] * p[2] + o0 > 0.0 ? 0u : tv;
+              in1 |= m[2][0] * p[0] + m[2][1] * p[1] + m[2][2] * p[2] + o1 > 0.0 ? 0u : tv;
+              in2 |= m[3][0] * p[0] + m[3][1] * p[1] + m[3][2] * p[2] + o2 > 0.0 ? 0u : tv;
             }
           }
-          need = not_above & not_below;
+          need = not_above & not_below & in0 & in1 & in2;
         }
       }
       if (!exhausted) {

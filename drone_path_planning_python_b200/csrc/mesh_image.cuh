@@ -37,6 +37,7 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
   unsigned long long* imask = (unsigned long long*)(base + layout->off_mask);
   unsigned* ivtri = (unsigned*)(base + layout->off_vtri);
   float* ifbox = (float*)(base + layout->off_fbox);
+  double* iedge = (double*)(base + layout->off_edge);
   for (int t = 0; t < T && t < 32; ++t)
     for (int c = 0; c < 3; ++c) ivtri[idx[3 * t + c]] |= 1u << t;
   memcpy(itri, tri, sizeof(double) * 9 * (size_t)T);
@@ -82,6 +83,25 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
     pl[1] = f1[2] * f2[0] - f1[0] * f2[2];
     pl[2] = f1[0] * f2[1] - f1[1] * f2[0];
     pl[3] = pl[0] * q[0] + pl[1] * q[1] + pl[2] * q[2];
+    // the three planes through the edges, perpendicular to the triangle: m_k = +-n x (Q_{k+1} - Q_k)
+    // pointing away from the opposite corner.  A point set with m_k . x > m_k . Q_k throughout is
+    // separated from the (closed) triangle.  The offset carries a slack far above the rounding of
+    // the dot products and far below any length that matters, so the cull errs towards testing.
+    double scale = 1.0;
+    for (int c = 0; c < 9; ++c) if (fabs(q[c]) > scale) scale = fabs(q[c]);
+    for (int k = 0; k < 3; ++k) {
+      const double* a = q + 3 * k;
+      const double* b = q + 3 * ((k + 1) % 3);
+      const double* o = q + 3 * ((k + 2) % 3);
+      const double ed[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+      double m[3] = {pl[1] * ed[2] - pl[2] * ed[1], pl[2] * ed[0] - pl[0] * ed[2], pl[0] * ed[1] - pl[1] * ed[0]};
+      if (m[0] * (o[0] - a[0]) + m[1] * (o[1] - a[1]) + m[2] * (o[2] - a[2]) > 0.0) {
+        m[0] = -m[0]; m[1] = -m[1]; m[2] = -m[2];
+      }
+      double* out = iedge + 12 * t + 4 * k;
+      out[0] = m[0]; out[1] = m[1]; out[2] = m[2];
+      out[3] = (m[0] * a[0] + m[1] * a[1] + m[2] * a[2]) + 1e-10 * (fabs(m[0]) + fabs(m[1]) + fabs(m[2])) * 2.0 * scale;
+    }
   }
   free(idx);
   free(uv);

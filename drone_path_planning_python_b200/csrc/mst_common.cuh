@@ -80,11 +80,13 @@ struct MeshView {
   const unsigned long long* mask;  // per triangle: bits of its (first 64) unique vertices
   const unsigned* vtri;            // per unique vertex: bits of the (first 32) triangles that use it
   const float* fbox;               // per triangle, 8 floats: the AABB rounded OUTWARD (min xyz, max xyz, 2 pad)
+  const double* edge;              // per triangle, 3 x (mx, my, mz, c): in-plane outward normal of edge k and its
+                                   // offset, so that m . x - c > 0 only for points beyond that edge's line
 };
 
 struct MeshLayout {
   int T, V;
-  size_t off_box, off_plane, off_vert, off_idx, off_mask, off_vtri, off_fbox, bytes;  // byte offsets from base
+  size_t off_box, off_plane, off_vert, off_idx, off_mask, off_vtri, off_fbox, off_edge, bytes;  // byte offsets from base
 };
 
 __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
@@ -101,6 +103,7 @@ __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
   L.off_vtri = o;  o += sizeof(unsigned) * (size_t)V;
   o = (o + 15) & ~(size_t)15;
   L.off_fbox = o;  o += sizeof(float) * 8 * (size_t)T;
+  L.off_edge = o;  o += sizeof(double) * 12 * (size_t)T;
   L.bytes = (o + 15) & ~(size_t)15;
   return L;
 }
@@ -117,6 +120,7 @@ __host__ __device__ __forceinline__ MeshView mesh_view(const void* base, const M
   v.mask = (const unsigned long long*)(b + L.off_mask);
   v.vtri = (const unsigned*)(b + L.off_vtri);
   v.fbox = (const float*)(b + L.off_fbox);
+  v.edge = (const double*)(b + L.off_edge);
   return v;
 }
 

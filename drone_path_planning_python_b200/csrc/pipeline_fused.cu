@@ -63,7 +63,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
   if (engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
   __syncthreads();
-  double* tables = nv + (engine ? ev.T * rb.V : 0);
+  double* tables = nv + (engine ? collide_table_doubles(ev.T, rb.V) : 0);
   double* knots = tables + warp * FUSED_WT * (n + 2);
   double* dts = knots + FUSED_WT * (n + 1);
   // thr[WT][n]: first sample index of pieces 1 .. n-1, and (when the launcher found room: TAB)
@@ -229,7 +229,7 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
   const bool tab = n <= 255 && S <= 1024;
   const size_t per_traj = sizeof(double) * (size_t)(n + 2) + sizeof(int) * (size_t)n + (tab ? (size_t)S : 0);
   while (FUSED_WT > 1 && FUSED_WARPS * FUSED_WT * per_traj > 24 * 1024) FUSED_WT /= 2;
-  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * (size_t)env->T * robot->V +
+  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * collide_table_doubles(env->T, robot->V) +
                       FUSED_WARPS * FUSED_WT * per_traj;
   auto kern = K == 3 ? (tab ? sample_collide_kernel<3, true> : sample_collide_kernel<3, false>)
                      : (tab ? sample_collide_kernel<4, true> : sample_collide_kernel<4, false>);
