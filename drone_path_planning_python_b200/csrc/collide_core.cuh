@@ -280,7 +280,8 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
 constexpr int COLLIDE_MAX_V = 32;    // unique robot vertices the bit masks can hold
 constexpr int COLLIDE_MAX_TR = 32;   // robot triangles the cursor's bit mask can hold
 constexpr int COLLIDE_RING = 64;     // poses per warp ring (a power of two, >= 2 * 32)
-constexpr int COLLIDE_ROUNDS = 2;    // candidates tested per pose and drain
+constexpr int COLLIDE_ROUNDS = 2;    // candidates tested per pose and drain (at most)
+constexpr int COLLIDE_MIN_LANES = 12; // undecided poses a drain needs to run another round
 
 template <int POSE> struct PoseDim { static constexpr int N = POSE == 0 ? 3 : (POSE == 1 ? 5 : 7); };
 
@@ -416,7 +417,15 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
   for (int round = 0; round < COLLIDE_ROUNDS; ++round) {
     bool have = false;
     int r = 0;
-    if (!hit && !exhausted) {
+    // later rounds only while enough poses of the batch are still undecided to fill the lanes:
+    // most poses are decided by their first candidate, and a round for a handful of lanes
+    // costs as much as one for 32 (they wait in the ring for a denser batch instead)
+    bool go = true;
+    if (round > 0) {
+      __syncwarp();
+      go = __popc(__ballot_sync(0xffffffffu, !hit && !exhausted)) >= COLLIDE_MIN_LANES;
+    }
+    if (go && !hit && !exhausted) {
       // Advance the cursor to the next candidate pair.  Keep this loop SINGLE-EXIT: a version
       // with `break` / `continue` compiled (nvcc 12.9, sm_100a) to BSSY.RELIABLE/BREAK control
       // flow that left the warp split at the ballot of the re-queue below — ptxas emits that
