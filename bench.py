@@ -233,6 +233,8 @@ def run_ours(args):
     # fallback: NCCL all_gather_into_tensor (distributed.ChunkedAllGather).
     from drone_path_planning_python_b200.distributed import ChunkedAllGather, PeerPushAllGather
     gather, gather_kind, n_chunks = None, None, 1
+    if args.gather_chunks <= 0:
+        args.gather_chunks = 4 if world == 2 else 2
     if world > 1:
         if args.gather == "push":
             try:
@@ -327,7 +329,7 @@ def run_ours(args):
     achieved = B * dom_bytes / (dom_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/ (ncu --set full,
     # 262,144 trajectories per launch, cold L2), scaled to this launch's trajectory count
-    traffic_per_traj = (525.209344e6 + 26.705920e6) / 262144
+    traffic_per_traj = (541.113344e6 + 30.006528e6) / 262144
 
     # --- end to end through HOST buffers (pinned), copies inside the timed region ----------
     hp = HostPipeline(N_SEG, K_AX, S_SAMPLES, robot, env, chunk=args.e2e_chunk)
@@ -408,7 +410,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--traj", type=int, default=TRAJ_PER_GPU, help="trajectories per GPU per step")
-    ap.add_argument("--gather-chunks", type=int, default=2)
+    ap.add_argument("--gather-chunks", type=int, default=0,
+                    help="chunks of the overlapped all-gather (0: 4 at 2 GPUs where the kernels still matter, "
+                         "2 beyond, where few large NVLink copies win; profiles/r1_scaling.md)")
     ap.add_argument("--gather", choices=["push", "nccl"], default="push")
     ap.add_argument("--push-streams", type=int, default=1)
     ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
