@@ -34,7 +34,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(PKG, "build_ptxas.log")
     with open(log, "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        # registers / spills / shared memory per kernel (-Xptxas -v); compile times dropped so that
+        # the tracked log only changes when the code does
+        text = "\n".join(l for l in (proc.stdout + proc.stderr).splitlines() if "Compile time" not in l)
+        fh.write(" ".join(cmd) + "\n" + text + "\n")
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
