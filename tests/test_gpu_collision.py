@@ -54,6 +54,38 @@ def test_collide_poses_vs_oracle(env_name, dim):
     assert 0.02 < ref.mean() < 0.9     # both outcomes are exercised
 
 
+@pytest.mark.parametrize("env_name", ["env-scene-ltu-experiment", "env-scene-hole-narrow"])
+@pytest.mark.parametrize("dim", [3, 4])
+def test_poses_grazing_triangle_edges_vs_oracle(env_name, dim):
+    """The cursor culls robot triangles that lie wholly beyond one of an env triangle's edge
+    planes.  Poses that put a robot vertex within millimetres of an env triangle's edge (inside,
+    outside, along it) are where a wrong cull would flip an answer; 56-triangle scenes also walk
+    two 32-triangle blocks of the box mask."""
+    from oracle import collision_oracle as co
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(77 + dim + len(env_name))
+    robot_tris, env_tris = _soup("custom_triangle_robot"), _soup(env_name)
+    robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
+    P = 4000
+    verts = np.unique(robot_tris.reshape(-1, 3), axis=0)
+    e = rng.integers(0, len(env_tris), P)
+    k = rng.integers(0, 3, P)
+    a, b = env_tris[e, k], env_tris[e, (k + 1) % 3]
+    on_edge = a + rng.uniform(-0.1, 1.1, (P, 1)) * (b - a)
+    yaw = rng.uniform(-np.pi, np.pi, P) if dim == 4 else np.zeros(P)
+    v = verts[rng.integers(0, len(verts), P)]
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    v_world = np.stack([c * v[:, 0] - s_ * v[:, 1], s_ * v[:, 0] + c * v[:, 1], v[:, 2]], axis=1)
+    pos = on_edge - v_world + rng.normal(0, 1.0, (P, 3)) * 10.0 ** rng.uniform(-6, -1, (P, 1))
+    poses4 = np.concatenate([pos, yaw[:, None]], axis=1)
+    hit = mst.collide_poses(robot, env, pos if dim == 3 else poses4).cpu().numpy()
+    ref, margin = co.collide_poses(robot_tris, env_tris, poses4, with_margin=True)
+    clear = np.abs(margin) > EPS
+    assert clear.mean() > 0.9
+    assert np.array_equal(hit[clear], ref[clear])
+    assert 0.05 < ref.mean() < 0.999
+
+
 def test_collide_translation_only_and_degenerate_robot():
     from oracle import collision_oracle as co
     import drone_path_planning_python_b200 as mst

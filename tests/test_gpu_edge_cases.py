@@ -134,3 +134,32 @@ def test_sample_count_not_multiple_of_32_and_single_trajectory():
         pos = mst.sample_batch(res.coef, res.dur, S=S)
         hit = mst.collide_poses(robot, env, pos.reshape(-1, 3)).reshape(B, S)
         assert torch.equal(res.hit, hit) and torch.equal(res.any_hit, hit.amax(dim=1))
+
+
+@pytest.mark.parametrize("n,S,K", [(1, 100, 3), (10, 1500, 3), (10, 1024, 4), (30, 64, 3), (300, 40, 3),
+                                    (7, 31, 4), (12, 2, 3)])
+def test_fused_piece_lookup_equals_sampler(n, S, K):
+    """The fused kernel finds a sample's piece through per-trajectory tables (first-sample
+    thresholds, and a piece-of-sample byte table when n <= 255 and S <= 1024; a bisection over
+    the thresholds otherwise).  Whatever the path, its flags must equal "sample with
+    mst_sample_batch, then collide" — including zero-length pieces, where several thresholds
+    coincide, a zero total duration, and tiles of every size."""
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(1000 * n + S)
+    robot, env = mst.Mesh(_soup("custom_triangle_robot")), mst.Mesh(_soup("env-scene-ltu-experiment"))
+    B = 77
+    dur = rng.uniform(0.1, 1.0, (B, n))
+    dur[rng.random((B, n)) < 0.2] = 0.0          # zero-length pieces (leading, trailing, in a row)
+    dur[3] = 0.0                                 # a trajectory of zero total duration
+    dur[4, :] = 0.0
+    dur[4, n // 2] = 0.7                         # everything in one piece
+    coef = np.zeros((B, n, K, 8))
+    coef[..., 0] = np.array([0.0, 3.5, 1.2, 0.3][:K]) + rng.normal(0, 0.6, (B, n, K))
+    coef[..., 1] = rng.normal(0, 1.0, (B, n, K))
+    coef[..., 2] = rng.normal(0, 0.5, (B, n, K))
+    hit, any_hit = mst.collide_trajectories(coef, dur, S, robot, env)
+    pos = mst.sample_batch(coef, dur, S=S)
+    want = mst.collide_poses(robot, env, pos.reshape(B * S, K)).reshape(B, S)
+    assert torch.equal(hit, want)
+    assert torch.equal(any_hit, want.amax(dim=1))
+    assert 0 < int(want.sum()) < B * S
