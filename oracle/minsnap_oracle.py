@@ -315,3 +315,58 @@ def snap_cost(coef, durations):
             d4 = P.polyder(np.asarray(coef[i, k], dtype=np.float64), 4)
             total += P.polyval(float(T), P.polyint(P.polymul(d4, d4)))
     return float(total)
+
+
+def optimize_time_allocation(waypoints, times, iters=8, line_search=6, rel_step=1e-4, min_fraction=0.1):
+    """Checker for ``drone_path_planning_python_b200.time_allocation`` (an extension: the reference
+    never searches over stamps, so there is nothing to pin this against — parity UNPINNED, the
+    two implementations are only checked against each other and against the properties of the
+    method).  One problem: ``waypoints[m, K]``, ``times[m]`` -> ``(times_new[m], cost[iters + 1])``.
+    Projected gradient descent on the durations, first stamp and total fixed: forward
+    differences along ``u_i = e_i - 1/n``, candidates ``T - cap / 2^k * g``, best one kept when
+    it lowers the snap cost."""
+    waypoints = np.asarray(waypoints, dtype=np.float64)
+    times = np.asarray(times, dtype=np.float64)
+    n = len(times) - 1
+
+    def cost(T):
+        t = np.concatenate([[times[0]], times[0] + np.cumsum(T)])
+        try:
+            coef, dur = solve_waypoints(waypoints, t)
+        except (np.linalg.LinAlgError, AssertionError):
+            return np.inf
+        c = snap_cost(coef, dur)
+        return c if np.isfinite(c) else np.inf
+
+    T = np.diff(times)
+    history = [cost(T)]
+    if n < 2:
+        return times.copy(), np.array(history * (iters + 1))
+    total = T.sum()
+    floor = min_fraction * total / n
+    h = rel_step * total / n
+    for _ in range(iters):
+        J0 = history[-1]
+        g = np.zeros(n)
+        for i in range(n):
+            u = -np.ones(n) / n
+            u[i] += 1.0
+            Ji = cost(T + h * u)
+            g[i] = (Ji - J0) / h if np.isfinite(Ji) else 0.0
+        g -= g.mean()
+        cap = 0.5 * max((T - floor).min(), 0.0) / max(np.abs(g).max(), 1e-300)
+        best_J, best_T = np.inf, T
+        for k in range(line_search):
+            cand = T - cap * 0.5 ** k * g
+            Jk = cost(cand)
+            if Jk < best_J:
+                best_J, best_T = Jk, cand
+        if best_J < J0:
+            T = best_T
+            history.append(best_J)
+        else:
+            history.append(J0)
+    out = np.concatenate([[times[0]], times[0] + np.cumsum(T)])
+    out[-1] = times[-1]
+    return out, np.array(history)
+

@@ -179,3 +179,22 @@ def test_c_restatement_equals_numpy_oracle():
             assert np.array_equal(build_oracle.c_collide_poses(robot, env, poses), ref)
             assert np.array_equal(build_oracle.c_collide_poses(robot, env, poses, prune=False), ref)
             assert 0.05 < ref.mean() < 0.95
+
+
+def test_time_allocation_checker_properties():
+    """The numpy checker of the time-allocation search (an extension with nothing in the reference
+    to pin it to): cost never increases, first stamp and total duration stay, durations respect
+    the floor, and evenly spaced collinear waypoints with uniform stamps stay put."""
+    from oracle import minsnap_oracle as mo
+    rng = np.random.default_rng(11)
+    n, K = 5, 3
+    wp = np.cumsum(rng.normal(0, 1, (n + 1, K)), axis=0)
+    t = np.concatenate([[0.0], np.cumsum(rng.uniform(0.6, 1.6, n))])
+    t_new, cost = mo.optimize_time_allocation(wp, t, iters=5)
+    assert (np.diff(cost) <= 0).all() and cost[-1] < 0.9 * cost[0]
+    assert t_new[0] == t[0] and t_new[-1] == t[-1]
+    assert (np.diff(t_new) >= 0.1 * t[-1] / n * (1 - 1e-12)).all()
+    line = np.linspace(0, 1, n + 1)[:, None] * np.array([1.0, -2.0, 0.5])
+    even = np.linspace(0.0, 5.0, n + 1)
+    t_even, cost_even = mo.optimize_time_allocation(line, even, iters=3)
+    assert cost_even[-1] <= cost_even[0]
