@@ -263,10 +263,13 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
 // work to avoid is everything after the first hit:
 //   * a pose enters the ring only if it passes the root-box culls (pose_near_environment);
 //   * draining 32 poses, each lane advances a CURSOR (env triangle e, bit mask of the robot
-//     triangles still to test against e) to its next candidate — the culls are the same
-//     exact-safe ones: env-triangle box, env plane against all unique robot vertices
-//     ("above"/"below" bit masks), robot triangles whose corner bits agree are skipped — and
-//     all lanes that have a candidate run the pair test together (interval form);
+//     triangles still to test against e, bit mask of the env triangles of e's block of 32
+//     whose box meets the robot's) to its next candidate — the culls are exact-safe ones:
+//     env-triangle boxes (one single-precision pass per block, bounds rounded outward), then
+//     the plane of e and its three edge planes against all unique robot vertices, kept as
+//     sets of robot triangles (a triangle is a candidate if it straddles the plane and is
+//     not wholly beyond an edge) — and all lanes that have a candidate run the pair test
+//     together (interval form);
 //   * after ROUNDS candidates a pose that is still undecided goes back to the tail of the
 //     ring WITH its cursor, so the next batch is dense again instead of 32 lanes waiting for
 //     the slowest one.
@@ -274,9 +277,9 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
 // all pairs: stopping early only skips pairs after a hit.
 //
 // POSE: 0 translation (x,y,z); 1 yaw (x,y,z,sin(yaw/2),cos(yaw/2)); 2 quaternion
-// (x,y,z,qx,qy,qz,qw).  nv (POSE 0 only): table nv[e][v] = n_e . v of env plane normals
-// against the robot's unique vertices — a translation leaves it constant, so the signed
-// distance of vertex v to plane e is one add.
+// (x,y,z,qx,qy,qz,qw).  nv (POSE 0 only): tables n_e . v and m_ek . v of the env planes and edge
+// planes against the robot's unique vertices (build_plane_vertex_table) — a translation leaves
+// them constant, so the signed distance of vertex v to a plane is one add.
 constexpr int COLLIDE_MAX_V = 32;    // unique robot vertices the bit masks can hold
 constexpr int COLLIDE_MAX_TR = 32;   // robot triangles the cursor's bit mask can hold
 constexpr int COLLIDE_RING = 64;     // poses per warp ring (a power of two, >= 2 * 32)
