@@ -160,17 +160,40 @@ __host__ __device__ inline bool robot_hits_env(const double* R, const double* T,
 }
 
 // ---------------------------------------------------------------------------------------
+// double -> float rounded towards -inf / +inf (conservative boxes)
+__host__ __device__ __forceinline__ float round_down_f(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2float_rd(x);
+#else
+  float f = (float)x;
+  return (double)f > x ? nextafterf(f, -INFINITY) : f;
+#endif
+}
+__host__ __device__ __forceinline__ float round_up_f(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2float_ru(x);
+#else
+  float f = (float)x;
+  return (double)f < x ? nextafterf(f, INFINITY) : f;
+#endif
+}
+
 // Culled mesh-mesh test used by the kernels.  Same answer as robot_hits_env (brute-force
 // SAT over all pairs) away from the touching boundary; every cull is a valid separating
 // axis in exact arithmetic:
 //   1. robot bounding sphere / box against the environment's root box;
-//   2. per environment triangle: robot box against the triangle's box;
-//   3. per environment triangle: the triangle's PLANE against ALL unique robot vertices at
-//      once (the plane is moved into the robot frame: 12 FMAs, then 3 FMAs per vertex) —
-//      this is SAT axis 2 (the env normal) shared by every robot triangle, recorded as
-//      "strictly above" / "strictly below" bit masks over the unique vertices;
-//   4. per robot triangle: skipped when its three corner bits are all above or all below;
+//   2. per environment triangle: robot box against the triangle's box (single precision, every
+//      bound rounded outward — conservative, the exact tests follow);
+//   3. per environment triangle: the triangle's PLANE and its three EDGE PLANES against ALL
+//      unique robot vertices at once (the planes are moved into the robot frame: 12 FMAs each,
+//      then 3 FMAs per vertex) — SAT axis 2 (the env normal) and the in-plane edge normals,
+//      shared by every robot triangle, recorded as "strictly above" / "strictly below" /
+//      "beyond edge k" bit masks over the unique vertices;
+//   4. per robot triangle: skipped when its three corner bits are all above, all below, or
+//      all beyond the same edge;
 //   5. the 17-axis SAT on the few surviving pairs.
+// This is the host-checkable statement of the culls the warp engine below applies (the engine
+// keeps them as sets of robot triangles and uses the interval pair test).
 // ROT = false: translation only (R = identity), the K = 3 pipeline.
 template <bool ROT>
 __host__ __device__ inline bool robot_hits_env_culled(const double* R, const double* T, const MeshView& rb,
@@ -201,34 +224,45 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
   }
   if (hi0 < root[0] || lo0 > root[3] || hi1 < root[1] || lo1 > root[4] || hi2 < root[2] || lo2 > root[5])
     return false;
+  const float flo0 = round_down_f(lo0), flo1 = round_down_f(lo1), flo2 = round_down_f(lo2);
+  const float fhi0 = round_up_f(hi0), fhi1 = round_up_f(hi1), fhi2 = round_up_f(hi2);
   for (int e = 0; e < ev.T; ++e) {
     const double* bx = ev.box + 6 * e;
-    if (hi0 < bx[0] || lo0 > bx[3] || hi1 < bx[1] || lo1 > bx[4] || hi2 < bx[2] || lo2 > bx[5]) continue;
-    // plane of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
+    const float* fb = ev.fbox + 8 * e;
+    if (fhi0 < fb[0] || flo0 > fb[3] || fhi1 < fb[1] || flo1 > fb[4] || fhi2 < fb[2] || flo2 > fb[5]) continue;
+    // planes of the env triangle in the robot frame: n.(R v + T) - d = (R^T n).v + (n.T - d)
     const double* pl = ev.plane + 4 * e;
-    double m0, m1, m2;
-    if (ROT) {
-      m0 = R[0] * pl[0] + R[3] * pl[1] + R[6] * pl[2];
-      m1 = R[1] * pl[0] + R[4] * pl[1] + R[7] * pl[2];
-      m2 = R[2] * pl[0] + R[5] * pl[1] + R[8] * pl[2];
-    } else {
-      m0 = pl[0]; m1 = pl[1]; m2 = pl[2];
+    const double* ed = ev.edge + 12 * e;
+    double m[4][3], off[4];
+    for (int j = 0; j < 4; ++j) {
+      const double* q = j == 0 ? pl : ed + 4 * (j - 1);
+      if (ROT) {
+        m[j][0] = R[0] * q[0] + R[3] * q[1] + R[6] * q[2];
+        m[j][1] = R[1] * q[0] + R[4] * q[1] + R[7] * q[2];
+        m[j][2] = R[2] * q[0] + R[5] * q[1] + R[8] * q[2];
+      } else {
+        m[j][0] = q[0]; m[j][1] = q[1]; m[j][2] = q[2];
+      }
+      off[j] = q[0] * T[0] + q[1] * T[1] + q[2] * T[2] - q[3];
     }
-    const double off = pl[0] * T[0] + pl[1] * T[1] + pl[2] * T[2] - pl[3];
-    unsigned long long above = 0ull, below = 0ull;
+    unsigned long long above = 0ull, below = 0ull, out0 = 0ull, out1 = 0ull, out2 = 0ull;
     for (int v = 0; v < rb.V; ++v) {
       const double* p = rb.vert + 3 * v;
-      const double dist = m0 * p[0] + m1 * p[1] + m2 * p[2] + off;
+      const double dist = m[0][0] * p[0] + m[0][1] * p[1] + m[0][2] * p[2] + off[0];
       above |= (unsigned long long)(dist > 0.0) << v;
       below |= (unsigned long long)(dist < 0.0) << v;
+      out0 |= (unsigned long long)(m[1][0] * p[0] + m[1][1] * p[1] + m[1][2] * p[2] + off[1] > 0.0) << v;
+      out1 |= (unsigned long long)(m[2][0] * p[0] + m[2][1] * p[1] + m[2][2] * p[2] + off[2] > 0.0) << v;
+      out2 |= (unsigned long long)(m[3][0] * p[0] + m[3][1] * p[1] + m[3][2] * p[2] + off[3] > 0.0) << v;
     }
     const unsigned long long all = rb.V >= 64 ? ~0ull : ((1ull << rb.V) - 1ull);
-    if (above == all || below == all) continue;
+    if (above == all || below == all || out0 == all || out1 == all || out2 == all) continue;
     const double* q = ev.tri + 9 * e;
     const V3 Q1 = {q[0], q[1], q[2]}, Q2 = {q[3], q[4], q[5]}, Q3 = {q[6], q[7], q[8]};
     for (int r = 0; r < rb.T; ++r) {
       const unsigned long long mk = rb.mask[r];
-      if ((above & mk) == mk || (below & mk) == mk) continue;
+      if ((above & mk) == mk || (below & mk) == mk || (out0 & mk) == mk || (out1 & mk) == mk || (out2 & mk) == mk)
+        continue;
       const double* pr = rb.tri + 9 * r;
       V3 P1, P2, P3;
       if (ROT) {
@@ -413,8 +447,8 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
   double R[9], lo[3], hi[3];
   pose_rotation<POSE>(pp, R);
   robot_world_box<POSE>(pp, R, rbb, lo, hi);
-  const float flo0 = __double2float_rd(lo[0]), flo1 = __double2float_rd(lo[1]), flo2 = __double2float_rd(lo[2]);
-  const float fhi0 = __double2float_ru(hi[0]), fhi1 = __double2float_ru(hi[1]), fhi2 = __double2float_ru(hi[2]);
+  const float flo0 = round_down_f(lo[0]), flo1 = round_down_f(lo[1]), flo2 = round_down_f(lo[2]);
+  const float fhi0 = round_up_f(hi[0]), fhi1 = round_up_f(hi[1]), fhi2 = round_up_f(hi[2]);
   bool hit = false, exhausted = !valid;
 #pragma unroll 1
   for (int round = 0; round < COLLIDE_ROUNDS; ++round) {
