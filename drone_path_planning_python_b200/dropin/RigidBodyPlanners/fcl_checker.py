@@ -62,15 +62,20 @@ class Fcl_mesh():
 def visualize_meshes(filenames):
     """Plot STL files (reference :62-82); matplotlib imported lazily."""
     from matplotlib import pyplot as plt
-    from mpl_toolkits import mplot3d
+    from mpl_toolkits.mplot3d.art3d import Poly3DCollection
 
-    figure = plt.figure()
-    axes = mplot3d.Axes3D(figure)
+    ax = plt.figure().add_subplot(projection="3d")
+    corners = []
     for filename in filenames:
-        axes.add_collection3d(mplot3d.art3d.Poly3DCollection(_meshio.read_stl(filename)))
-    axes.set_xlabel('X')
-    axes.set_ylabel('Y')
-    axes.set_zlabel('Z')
+        triangles = _meshio.read_stl(filename)
+        corners.append(triangles.reshape(-1, 3))
+        ax.add_collection3d(Poly3DCollection(triangles, alpha=0.6))
+    if corners:   # collections do not autoscale the axes
+        pts = np.concatenate(corners)
+        for setter, lo, hi in zip((ax.set_xlim, ax.set_ylim, ax.set_zlim), pts.min(0), pts.max(0)):
+            setter(lo, hi)
+    for label, setter in zip("XYZ", (ax.set_xlabel, ax.set_ylabel, ax.set_zlabel)):
+        setter(label)
     plt.show()
 
 

@@ -68,8 +68,8 @@ class Polynomial:
         coef = _padded(self.p).reshape(1, 1, 1, _NCOEF)
         return _host(_mst.sample_batch(coef, np.ones((1, 1)), ts=ts, deriv=deriv))[0, :, 0]
 
-    # compute and return derivative
     def derivative(self):
+        """d/dt as a new Polynomial (mst_poly_derivative)"""
         n = len(self.p)
         if n <= 1:
             return Polynomial([])
@@ -80,7 +80,7 @@ class Polynomial:
         return Polynomial([float(v) for v in d])
 
     def pol_coeffs_at_t(self, t):
-        # calculate the coefficients of the polynomial at time t
+        """The terms p[i] * t**i as an array (their sum is the value at t); mst_poly_terms_at_t."""
         assert t >= 0
         n = len(self.p)
         flat = np.asarray(self.p, dtype=np.float64).reshape(1, -1)
@@ -91,12 +91,12 @@ class Polynomial:
 
 
 class TrajectoryOutput:
+    """Flat outputs of one evaluation, all ``None`` until filled: ``pos`` / ``vel`` / ``acc`` (3-vectors in
+    m, m/s, m/s^2), ``omega`` (body rates, rad/s) and ``yaw`` (rad).  reference: uav_trajectory.py:39-45"""
+
     def __init__(self):
-        self.pos = None   # position [m]
-        self.vel = None   # velocity [m/s]
-        self.acc = None   # acceleration [m/s^2]
-        self.omega = None  # angular velocity [rad/s]
-        self.yaw = None   # yaw angle [rad]
+        for field in ("pos", "vel", "acc", "omega", "yaw"):
+            setattr(self, field, None)
 
 
 def _flat_to_output(row):
@@ -109,28 +109,19 @@ def _flat_to_output(row):
     return out
 
 
-# 4d single polynomial piece for x-y-z-yaw, includes duration.
 class Polynomial4D:
-    """reference: uav_trajectory.py:49-101"""
+    """One piece of an (x, y, z, yaw) trajectory with its duration.  reference: uav_trajectory.py:49-101"""
 
     def __init__(self, duration, px, py, pz, pyaw):
         self.duration = duration
-        self.px = Polynomial(px)
-        self.py = Polynomial(py)
-        self.pz = Polynomial(pz)
-        self.pyaw = Polynomial(pyaw)
+        self.px, self.py, self.pz, self.pyaw = (Polynomial(axis) for axis in (px, py, pz, pyaw))
 
     def _coef(self):
         return np.stack([_padded(self.px.p), _padded(self.py.p), _padded(self.pz.p), _padded(self.pyaw.p)])
 
-    # compute and return derivative
     def derivative(self):
-        return Polynomial4D(
-            self.duration,
-            self.px.derivative().p,
-            self.py.derivative().p,
-            self.pz.derivative().p,
-            self.pyaw.derivative().p)
+        axes = (self.px, self.py, self.pz, self.pyaw)
+        return Polynomial4D(self.duration, *(axis.derivative().p for axis in axes))
 
     def eval(self, t):
         assert t >= 0  # Polynomial.eval's assert in the reference
@@ -153,12 +144,10 @@ class Trajectory:
 
     def loadcsv(self, filename):
         # skiprows=1 although path_to_pol writes no header: kept
-        data = np.loadtxt(filename, delimiter=",",
-                          skiprows=1, usecols=range(33))
-        data = np.atleast_2d(data)
-        self.polynomials = [Polynomial4D(
-            row[0], row[1:9], row[9:17], row[17:25], row[25:33]) for row in data]
-        self.duration = np.sum(data[:, 0])
+        table = np.atleast_2d(np.loadtxt(filename, delimiter=",", skiprows=1, usecols=range(33)))
+        # a row is [duration | 8 x | 8 y | 8 z | 8 yaw]
+        self.polynomials = [Polynomial4D(r[0], *(r[1 + 8 * a:9 + 8 * a] for a in range(4))) for r in table]
+        self.duration = np.sum(table[:, 0])
         self._dev = None
 
     def _device_arrays(self):
@@ -188,15 +177,8 @@ class Trajectory:
 
 class PiecewisePolynomial():
     """
-    Piece-wise polynomial (reference: uav_trajectory.py:130-169).
-
-    Parameters
-    ----------
-    pols : list of Polynomial classes
-        All the polynomials used.
-
-    time_durations: list of floats
-        The duration of every piece
+    Piece-wise polynomial (reference: uav_trajectory.py:130-169): ``pols`` is the list of
+    ``Polynomial`` pieces in order, ``time_durations`` the list of their durations in seconds.
     """
 
     def __init__(self, pols: list, time_durations: list):
