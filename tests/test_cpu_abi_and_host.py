@@ -215,3 +215,78 @@ def test_interval_triangle_test_equals_sat_outside_the_touching_band():
         assert np.array_equal(hit, o17.astype(bool)), name        # the kernels' SAT is the oracle's SAT
         clear = np.abs(gap) > 1e-9
         assert np.array_equal(o17[clear], oi[clear]), name
+
+
+def _exact_triangles_meet(A, B):
+    """Do two closed, non-degenerate triangles share a point?  Decided in exact rational arithmetic
+    by a method that has nothing in common with a separating-axis test: two triangles meet iff an
+    edge of one meets the other triangle (closed segment against closed triangle; a segment lying
+    in the triangle's plane is handled in 2-D)."""
+    from fractions import Fraction as F
+    A = [[F(float(x)) for x in v] for v in A]
+    B = [[F(float(x)) for x in v] for v in B]
+    sub = lambda a, b: [a[i] - b[i] for i in range(3)]
+    dot = lambda a, b: a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+    cross = lambda a, b: [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+
+    def orient2(a, b, c):
+        return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
+
+    def point_in_tri2(p, t):
+        s = [orient2(t[i], t[(i + 1) % 3], p) for i in range(3)]
+        return all(x >= 0 for x in s) or all(x <= 0 for x in s)
+
+    def seg_seg2(p, q, a, b):
+        d1, d2 = orient2(a, b, p), orient2(a, b, q)
+        d3, d4 = orient2(p, q, a), orient2(p, q, b)
+        if d1 == 0 and d2 == 0 and d3 == 0 and d4 == 0:      # collinear: overlap of the ranges
+            k = 0 if p[0] != q[0] or a[0] != b[0] else 1
+            return max(min(p[k], q[k]), min(a[k], b[k])) <= min(max(p[k], q[k]), max(a[k], b[k]))
+        return (d1 * d2 <= 0) and (d3 * d4 <= 0)
+
+    def seg_tri(p, q, t):
+        n = cross(sub(t[1], t[0]), sub(t[2], t[0]))
+        dp, dq = dot(n, sub(p, t[0])), dot(n, sub(q, t[0]))
+        if (dp > 0 and dq > 0) or (dp < 0 and dq < 0):
+            return False
+        if dp == 0 and dq == 0:                               # in the plane: drop the dominant axis
+            k = max(range(3), key=lambda i: abs(n[i]))
+            keep = [i for i in range(3) if i != k]
+            P, Q = [p[i] for i in keep], [q[i] for i in keep]
+            T = [[v[i] for i in keep] for v in t]
+            return (point_in_tri2(P, T) or point_in_tri2(Q, T) or
+                    any(seg_seg2(P, Q, T[i], T[(i + 1) % 3]) for i in range(3)))
+        s = dp / (dp - dq)
+        x = [p[i] + s * (q[i] - p[i]) for i in range(3)]
+        side = [dot(cross(sub(t[(i + 1) % 3], t[i]), sub(x, t[i])), n) for i in range(3)]
+        return all(v >= 0 for v in side)
+
+    return (any(seg_tri(A[i], A[(i + 1) % 3], B) for i in range(3)) or
+            any(seg_tri(B[i], B[(i + 1) % 3], A) for i in range(3)))
+
+
+def test_sat_restatement_decides_exactly_whether_lattice_triangles_meet():
+    """On triangles with corners on a 1/8 lattice every product in the 17-axis test is exact in
+    double precision, so the restatement of FCL's triangle test must agree with the exact
+    answer for closed triangles on EVERY pair — touching at a corner, along an edge, coplanar
+    overlap included (the lattice makes those common).  This pins the predicate (closed sets,
+    touching counts) independently of any separating-axis reasoning; the C restatement and the
+    kernels' own SAT / interval forms are held to the same answers."""
+    from oracle import collision_oracle as co
+    rng = np.random.default_rng(2024)
+    N = 1500
+    tri = np.round(rng.uniform(-1.0, 1.0, (N, 2, 3, 3)) * 8) / 8
+    tri[N // 2:, :, :, 2] = np.round(tri[N // 2:, :, :, 2] * 0.3 * 8) / 8        # flat slabs: many coplanar pairs
+    area = np.linalg.norm(np.cross(tri[:, :, 1] - tri[:, :, 0], tri[:, :, 2] - tri[:, :, 0]), axis=-1)
+    tri = np.ascontiguousarray(tri[(area > 0).all(axis=1)])
+    N = len(tri)
+    want = np.array([_exact_triangles_meet(t[0], t[1]) for t in tri])
+    hit, gap = co.sat_pair(tri[:, 0], tri[:, 1])
+    touching = int((want & (gap == 0)).sum())
+    assert np.array_equal(hit, want)
+    assert 0.2 < want.mean() < 0.9 and touching > 20          # both outcomes and real touching cases
+    lib = _hostcheck()
+    o17, oi = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+    lib.hostcheck_tri_pairs(P(tri.ctypes.data), N, P(o17.ctypes.data), P(oi.ctypes.data))
+    assert np.array_equal(o17.astype(bool), want)             # the kernels' 17-axis form
+    assert np.array_equal(oi.astype(bool), want)              # and their interval form (SAT fallback when coplanar)

@@ -198,3 +198,4 @@ def test_time_allocation_checker_properties():
     even = np.linspace(0.0, 5.0, n + 1)
     t_even, cost_even = mo.optimize_time_allocation(line, even, iters=3)
     assert cost_even[-1] <= cost_even[0]
+
