@@ -290,3 +290,7 @@ def test_sat_restatement_decides_exactly_whether_lattice_triangles_meet():
     lib.hostcheck_tri_pairs(P(tri.ctypes.data), N, P(o17.ctypes.data), P(oi.ctypes.data))
     assert np.array_equal(o17.astype(bool), want)             # the kernels' 17-axis form
     assert np.array_equal(oi.astype(bool), want)              # and their interval form (SAT fallback when coplanar)
+    from oracle import build_oracle
+    still = np.zeros((1, 4))
+    c_says = np.array([build_oracle.c_collide_poses(t[0][None], t[1][None], still)[0] for t in tri[:400]])
+    assert np.array_equal(c_says.astype(bool), want[:400])    # the C restatement, one-triangle meshes
