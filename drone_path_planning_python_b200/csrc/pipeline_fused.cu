@@ -7,12 +7,12 @@
 // 208-215) and Fcl_checker.check_collision (src/RigidBodyPlanners/fcl_checker.py:93-100).
 //
 // Data flow: coefficients and durations come straight from the solver kernels' output
-// (still L2 resident: the host wrapper walks the batch in L2-sized chunks), both meshes
+// (pulled into L2 a few trajectories ahead of their use), both meshes
 // are staged once per CTA into shared memory with one bulk (TMA) copy each, sampled
 // positions never leave registers; only hit[B][S] (1 byte per sample, coalesced) and
 // any_hit[B] are written.
 //
-// Mapping: a WARP walks tiles of 4 trajectories; inside a tile the (trajectory, sample)
+// Mapping: a WARP walks tiles of (up to) 16 trajectories; inside a tile the (trajectory, sample)
 // pairs are flattened over the lanes, so a warp holds 32 CONSECUTIVE samples of one
 // trajectory (neighbouring poses: coefficient loads are warp-wide broadcasts, the broad
 // phase decisions mostly agree) and the narrow phase is compacted across the warp.
