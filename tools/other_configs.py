@@ -45,3 +45,12 @@ mst.optimize_time_allocation(wp,t,iters=1); torch.cuda.synchronize()
 t0=time.perf_counter(); tn,cost=mst.optimize_time_allocation(wp,t,iters=iters); torch.cuda.synchronize(); dt=time.perf_counter()-t0
 print("config2 time-allocation search: %d problems x %d pieces, %d iterations: %.1f ms (%.1f ms / iteration, %.1f M re-solves/s); median cost ratio %.3f" % (
     B, n, iters, dt*1e3, dt*1e3/iters, B*(n+6)*iters/dt/1e6, float((cost[-1]/cost[0]).median())))
+# the benchmark's pipeline with the yaw axis as well (K = 4: rotated culls instead of the translation tables)
+B,n,K,S=1<<20,10,4,100
+T=rng.uniform(0.5,2,(B,n)); t=torch.as_tensor(np.concatenate([np.zeros((B,1)),np.cumsum(T,1)],1),device='cuda')
+wp4=np.zeros((B,n+1,K)); wp4[:,:,:3]=rng.uniform([-2.2,2.8,0.5],[2.2,5.0,2.5],(B,1,3))+np.cumsum(rng.normal(0,0.3,(B,n+1,3)),1)
+wp4[:,:,3]=np.cumsum(rng.normal(0,0.1,(B,n+1)),1)
+wp4=torch.as_tensor(wp4,device='cuda')
+out=mst.pipeline(wp4,t,S,robot,env)
+ms=timeit(lambda: mst.pipeline(wp4,t,S,robot,env,out=out),5)
+print("pipeline K=4 (x,y,z,yaw), 1M trajectories: %.2f ms -> %.1f M trajectories/s, any-hit rate %.2f" % (ms, B/ms/1e3, float(out.any_hit.float().mean())))
