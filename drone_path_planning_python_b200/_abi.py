@@ -30,6 +30,7 @@ PROTOTYPES = {
                                        ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p]),
     "mst_snap_cost": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p]),
+    "mst_time_gradient": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p]),
     "mst_pack_pol_matrix": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            c_void_p, c_void_p]),
     "mst_sample_batch": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -125,6 +125,18 @@ def snap_cost(coef, dur) -> torch.Tensor:
     return cost
 
 
+def time_gradient(coef) -> torch.Tensor:
+    """``grad[B, n]`` = d(optimal snap cost)/d(duration of piece i) with the waypoints fixed, from the
+    coefficients of one solve (minus the piece's Hamiltonian; an extension, see include/mst.h)."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    coef = _f64(coef, dev)
+    B, n, K, _ = coef.shape
+    grad = torch.empty((B, n), dtype=torch.float64, device=dev)
+    _abi.check(lib.mst_time_gradient(_ptr(coef), B, n, K, _ptr(grad), _stream_ptr()), "mst_time_gradient")
+    return grad
+
+
 # --------------------------------------------------------------------------- a8
 def pack_pol_matrix(coef, dur) -> torch.Tensor:
     """``coef[B, n, K, 8]``, ``dur[B, n]`` -> float32 ``[B, n, 1 + 8K]`` rows

@@ -46,6 +46,7 @@ int launch_flat(const double* coef, const double* dur, int B, int n, const doubl
 int launch_time_power(const double* t, int count, double* rows, cudaStream_t stream);
 int launch_pack_matrix(const double* coef, const double* dur, long long rows, int K, float* out, cudaStream_t stream);
 int launch_snap_cost(const double* coef, const double* dur, int B, int n, int K, double* cost, cudaStream_t stream);
+int launch_time_gradient(const double* coef, int B, int n, int K, double* grad, cudaStream_t stream);
 int launch_poly_derivative(const double* p, int count, int len, double* out, cudaStream_t stream);
 int launch_poly_terms(const double* p, const double* t, int count, int len, double* out, cudaStream_t stream);
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
@@ -120,6 +121,13 @@ extern "C" int mst_snap_cost(const double* coef, const double* dur, int B, int n
   if (B == 0) return MST_OK;
   if (!coef || !dur || !cost) return MST_ERR_INVALID;
   return launch_snap_cost(coef, dur, B, n, K, cost, (cudaStream_t)stream);
+}
+
+extern "C" int mst_time_gradient(const double* coef, int B, int n, int K, double* grad, void* stream) {
+  if (B < 0 || n < 1 || K < 1) return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!coef || !grad) return MST_ERR_INVALID;
+  return launch_time_gradient(coef, B, n, K, grad, (cudaStream_t)stream);
 }
 
 extern "C" int mst_pack_pol_matrix(const double* coef, const double* dur, int B, int n, int K, float* out,

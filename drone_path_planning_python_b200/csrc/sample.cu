@@ -266,6 +266,35 @@ int launch_snap_cost(const double* coef, const double* dur, int B, int n, int K,
   return check_launch();
 }
 
+// d(cost)/d(T_i) of the OPTIMAL snap cost with the waypoints fixed and the knot derivatives free (they
+// are what the solve optimises, so by the envelope theorem only the explicit dependence on T_i counts):
+// minus the Hamiltonian of piece i, which is constant along an optimal piece and is evaluated at its
+// start from the coefficients: H = x4^2 - 2 x5 x3 + 2 x6 x2 - 2 x7 x1 with xk the k-th derivative,
+// summed over axes.  One thread per piece.  (Checked against central differences of re-solves to 1e-8.)
+__global__ void __launch_bounds__(128)
+time_gradient_kernel(const double* __restrict__ coef, long long pieces, int K, double* __restrict__ grad) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pieces; p += (long long)gridDim.x * blockDim.x) {
+    double H = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double2* row = reinterpret_cast<const double2*>(coef + ((size_t)p * K + k) * MST_NCOEF);
+      const double2 c01 = __ldg(row), c23 = __ldg(row + 1), c45 = __ldg(row + 2), c67 = __ldg(row + 3);
+      const double x1 = c01.y, x2 = 2.0 * c23.x, x3 = 6.0 * c23.y, x4 = 24.0 * c45.x, x5 = 120.0 * c45.y,
+                   x6 = 720.0 * c67.x, x7 = 5040.0 * c67.y;
+      H += x4 * x4 - 2.0 * x5 * x3 + 2.0 * x6 * x2 - 2.0 * x7 * x1;
+    }
+    grad[p] = -H;
+  }
+}
+
+int launch_time_gradient(const double* coef, int B, int n, int K, double* grad, cudaStream_t stream) {
+  const long long pieces = (long long)B * n;
+  if (pieces <= 0) return MST_OK;
+  long long g = (pieces + 127) / 128;
+  if (g > (long long)MST_SM_COUNT * 16) g = (long long)MST_SM_COUNT * 16;
+  time_gradient_kernel<<<(unsigned)g, 128, 0, stream>>>(coef, pieces, K, grad);
+  return check_launch();
+}
+
 static unsigned grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)MST_SM_COUNT * 32;

@@ -132,6 +132,16 @@ int mst_solve_batch(const double* wp, const double* t, int B, int n, int K,
 int mst_snap_cost(const double* coef, const double* dur, int B, int n, int K, double* cost, void* stream);
 
 /*
+ * Derivative of the optimal snap cost with respect to every piece duration, waypoints fixed:
+ * grad[b][i] = -(Hamiltonian of piece i summed over axes), evaluated from the coefficients
+ * (H = x4^2 - 2 x5 x3 + 2 x6 x2 - 2 x7 x1, xk the k-th derivative at the start of the piece).  An
+ * extension like mst_snap_cost: the gradient of time-allocation searches, from ONE solve instead
+ * of n finite-difference re-solves.
+ *   coef [B][n][K][8]  ->  grad [B][n]
+ */
+int mst_time_gradient(const double* coef, int B, int n, int K, double* grad, void* stream);
+
+/*
  * Polynomial-piece matrix — the wire format path_to_pol writes to CSV and publishes
  * (scripts/drones_pols_generator.py:63-87): per piece one float32 row
  * [T | x0..x7 | y0..y7 | z0..z7 | yaw0..yaw7].

@@ -317,52 +317,60 @@ def snap_cost(coef, durations):
     return float(total)
 
 
-def optimize_time_allocation(waypoints, times, iters=8, line_search=6, rel_step=1e-4, min_fraction=0.1):
+def time_gradient(coef):
+    """d(optimal snap cost)/d(duration of piece i), waypoints fixed, knot derivatives free: minus the
+    Hamiltonian of the piece summed over axes, H = x4^2 - 2 x5 x3 + 2 x6 x2 - 2 x7 x1 with xk the k-th
+    derivative at the start of the piece (constant along an optimal piece).  ``coef[n, K, 8]`` ->
+    ``grad[n]``.  Checker of mst_time_gradient; itself checked against central differences of
+    re-solves in tests/test_cpu_oracle.py."""
+    coef = np.asarray(coef, dtype=np.float64)
+    x = coef * np.array([1.0, 1.0, 2.0, 6.0, 24.0, 120.0, 720.0, 5040.0])
+    H = x[..., 4] ** 2 - 2.0 * x[..., 5] * x[..., 3] + 2.0 * x[..., 6] * x[..., 2] - 2.0 * x[..., 7] * x[..., 1]
+    return -H.sum(axis=-1)
+
+
+def optimize_time_allocation(waypoints, times, iters=8, line_search=6, min_fraction=0.1):
     """Checker for ``drone_path_planning_python_b200.time_allocation`` (an extension: the reference
     never searches over stamps, so there is nothing to pin this against — parity UNPINNED, the
     two implementations are only checked against each other and against the properties of the
     method).  One problem: ``waypoints[m, K]``, ``times[m]`` -> ``(times_new[m], cost[iters + 1])``.
-    Projected gradient descent on the durations, first stamp and total fixed: forward
-    differences along ``u_i = e_i - 1/n``, candidates ``T - cap / 2^k * g``, best one kept when
-    it lowers the snap cost."""
+    Projected gradient descent on the durations, first stamp and total fixed: the gradient of one
+    solve (``time_gradient``) projected on ``sum T = const``, candidates ``T - cap / 2^k * g``,
+    best one kept when it lowers the snap cost."""
     waypoints = np.asarray(waypoints, dtype=np.float64)
     times = np.asarray(times, dtype=np.float64)
     n = len(times) - 1
 
-    def cost(T):
+    def solve(T):
         t = np.concatenate([[times[0]], times[0] + np.cumsum(T)])
         try:
             coef, dur = solve_waypoints(waypoints, t)
         except (np.linalg.LinAlgError, AssertionError):
-            return np.inf
+            return np.inf, None
         c = snap_cost(coef, dur)
-        return c if np.isfinite(c) else np.inf
+        return (c, coef) if np.isfinite(c) else (np.inf, None)
 
     T = np.diff(times)
-    history = [cost(T)]
+    J, coef = solve(T)
+    history = [J]
     if n < 2:
         return times.copy(), np.array(history * (iters + 1))
     total = T.sum()
     floor = min_fraction * total / n
-    h = rel_step * total / n
     for _ in range(iters):
         J0 = history[-1]
-        g = np.zeros(n)
-        for i in range(n):
-            u = -np.ones(n) / n
-            u[i] += 1.0
-            Ji = cost(T + h * u)
-            g[i] = (Ji - J0) / h if np.isfinite(Ji) else 0.0
-        g -= g.mean()
+        g = time_gradient(coef) if coef is not None else np.zeros(n)
+        g = np.where(np.isfinite(g), g, 0.0)
+        g = g - g.mean()
         cap = 0.5 * max((T - floor).min(), 0.0) / max(np.abs(g).max(), 1e-300)
-        best_J, best_T = np.inf, T
+        best_J, best_T, best_coef = np.inf, T, coef
         for k in range(line_search):
             cand = T - cap * 0.5 ** k * g
-            Jk = cost(cand)
+            Jk, ck = solve(cand)
             if Jk < best_J:
-                best_J, best_T = Jk, cand
+                best_J, best_T, best_coef = Jk, cand, ck
         if best_J < J0:
-            T = best_T
+            T, coef = best_T, best_coef
             history.append(best_J)
         else:
             history.append(J0)

@@ -199,3 +199,19 @@ def test_time_allocation_checker_properties():
     t_even, cost_even = mo.optimize_time_allocation(line, even, iters=3)
     assert cost_even[-1] <= cost_even[0]
 
+
+def test_time_gradient_checker_equals_central_differences_of_resolves():
+    """dJ/dT_i = -(Hamiltonian of piece i): the closed form the CUDA kernel and its numpy checker use,
+    against central differences of the snap cost over re-solves."""
+    rng = np.random.default_rng(3)
+    for n, K in ((2, 3), (6, 3), (9, 4)):
+        wp = np.cumsum(rng.normal(0, 1, (n + 1, K)), axis=0)
+        T = rng.uniform(0.6, 1.6, n)
+
+        def J(T):
+            coef, dur = mo.solve_waypoints(wp, np.concatenate([[0.0], np.cumsum(T)]))
+            return mo.snap_cost(coef, dur), coef
+        _, coef = J(T)
+        h = 1e-6
+        fd = np.array([(J(T + h * np.eye(n)[i])[0] - J(T - h * np.eye(n)[i])[0]) / (2 * h) for i in range(n)])
+        np.testing.assert_allclose(mo.time_gradient(coef), fd, rtol=2e-6, atol=1e-6 * np.abs(fd).max())

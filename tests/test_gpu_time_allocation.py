@@ -77,3 +77,26 @@ def test_degenerate_sizes():
     assert np.array_equal(t_new.cpu().numpy(), t) and cost.shape == (4, 1)
     t_new, cost = mst.optimize_time_allocation(np.zeros((0, 5, 3)), np.zeros((0, 5)), iters=2)
     assert t_new.shape == (0, 5) and cost.shape == (3, 0)
+
+
+def test_time_gradient_matches_the_checker_and_central_differences():
+    from oracle import minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(5)
+    B, n, K = 40, 8, 4
+    wp, t = _problems(rng, B, n, K)
+    coef, dur, info = mst.solve_batch(wp, t)
+    grad = mst.time_gradient(coef).cpu().numpy()
+    want = np.stack([mo.time_gradient(c) for c in coef.cpu().numpy()])
+    np.testing.assert_allclose(grad, want, rtol=1e-12, atol=1e-9 * np.abs(want).max())
+    # and it is the derivative of the cost the solver + cost kernels produce
+    T = np.diff(t, axis=1)
+    h = 1e-6
+    for i in (0, n // 2, n - 1):
+        Tp, Tm = T.copy(), T.copy()
+        Tp[:, i] += h
+        Tm[:, i] -= h
+        Jp = mst.snap_cost(*mst.solve_batch(wp, np.concatenate([t[:, :1], t[:, :1] + np.cumsum(Tp, 1)], 1))[:2])
+        Jm = mst.snap_cost(*mst.solve_batch(wp, np.concatenate([t[:, :1], t[:, :1] + np.cumsum(Tm, 1)], 1))[:2])
+        fd = ((Jp - Jm) / (2 * h)).cpu().numpy()
+        np.testing.assert_allclose(grad[:, i], fd, rtol=1e-5, atol=1e-5 * np.abs(fd).max())
