@@ -234,7 +234,7 @@ def run_ours(args):
     from drone_path_planning_python_b200.distributed import ChunkedAllGather, PeerPushAllGather
     gather, gather_kind, n_chunks = None, None, 1
     if args.gather_chunks <= 0:
-        args.gather_chunks = 4 if world == 2 else 2
+        args.gather_chunks = 4 if world <= 4 else 2
     if world > 1:
         if args.gather == "push":
             try:
@@ -411,8 +411,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--traj", type=int, default=TRAJ_PER_GPU, help="trajectories per GPU per step")
     ap.add_argument("--gather-chunks", type=int, default=0,
-                    help="chunks of the overlapped all-gather (0: 4 at 2 GPUs where the kernels still matter, "
-                         "2 beyond, where few large NVLink copies win; profiles/r1_scaling.md)")
+                    help="chunks of the overlapped all-gather (0: 4 up to 4 GPUs where the kernels still matter, "
+                         "2 at 8, where few large NVLink copies win; profiles/r1_scaling.md)")
     ap.add_argument("--gather", choices=["push", "nccl"], default="push")
     ap.add_argument("--push-streams", type=int, default=1)
     ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
