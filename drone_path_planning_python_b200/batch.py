@@ -29,6 +29,16 @@ def _f64(x, device) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64)), device=device)
 
 
+def _check_out(name: str, x, shape, dtype, device) -> None:
+    """Caller-supplied output buffers go to the kernels as raw pointers: refuse anything the
+    kernels would write out of bounds or mis-stride."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.device != device:
+        raise ValueError("%s must be a CUDA tensor on %s" % (name, device))
+    if x.dtype != dtype or tuple(x.shape) != tuple(shape) or not x.is_contiguous():
+        raise ValueError("%s must be a contiguous %s tensor of shape %s (got %s %s)"
+                         % (name, dtype, tuple(shape), x.dtype, tuple(x.shape)))
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -206,6 +216,8 @@ def flat_outputs(coef, dur, ts=None, S: Optional[int] = None, mode: str = "traje
         tsd = _f64(ts, dev)
         per = 1 if tsd.dim() == 2 else 0
         S = tsd.shape[-1]
+        if per and tsd.shape[0] != B:
+            raise ValueError("per-trajectory ts must be [B, S]")
     out = torch.empty((B, S, 13), dtype=torch.float64, device=dev)
     status = torch.empty((B, S), dtype=torch.uint8, device=dev)
     rc = lib.mst_flat_outputs(_ptr(coef), _ptr(dur), B, n, _ptr(tsd), per, S, _MODES[mode], _ptr(out),
@@ -337,6 +349,12 @@ def pipeline(wp, t, S: int, robot: Mesh, env: Mesh, share_time_group: int = 1, s
         raise IndexError("need at least two waypoints")
     if G < 1 or B % G != 0 or t.shape[0] != B // G or t.shape[1] != m:
         raise ValueError("t must be [B/share_time_group, n+1]")
+    if out is not None:
+        _check_out("out.coef", out.coef, (B, n, K, 8), torch.float64, dev)
+        _check_out("out.dur", out.dur, (B, n), torch.float64, dev)
+        _check_out("out.info", out.info, (B,), torch.int32, dev)
+        _check_out("out.hit", out.hit, (B, S), torch.uint8, dev)
+        _check_out("out.any_hit", out.any_hit, (B,), torch.uint8, dev)
     if out is None:
         out = PipelineResult(torch.empty((B, n, K, 8), dtype=torch.float64, device=dev),
                              torch.empty((B, n), dtype=torch.float64, device=dev),

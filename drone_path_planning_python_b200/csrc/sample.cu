@@ -145,7 +145,9 @@ flat_kernel(const double* __restrict__ coef, const double* __restrict__ dur, lon
         len = derive_once(c, len);
       }
     }
-    // thrust direction and body axes, same order of operations as the numpy code
+    // thrust direction and body axes, the numpy code's formulas; this file is built with the default
+    // -fmad=true, so the dot / cross / norm products below may be FMA-contracted: omega agrees with
+    // numpy to ~1e-11 relative, not bit for bit (pos / vel / acc / yaw above are the exact Horner)
     const double th0 = val[0][2], th1 = val[1][2], th2 = val[2][2] + 9.81;
     const double tn = sqrt(th0 * th0 + th1 * th1 + th2 * th2);
     const double zb0 = th0 / tn, zb1 = th1 / tn, zb2 = th2 / tn;
@@ -172,41 +174,44 @@ flat_kernel(const double* __restrict__ coef, const double* __restrict__ dur, lon
 
 // rows[count][8][8]: derivative j, power k -> k!/(k-j)! * t^(k-j)
 __global__ void time_power_kernel(const double* __restrict__ t, int count, double* __restrict__ rows) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= count * 64) return;
-  const int a = idx >> 6, j = (idx >> 3) & 7, k = idx & 7;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)count * 64) return;
+  const long long a = idx >> 6;
+  const int j = (int)(idx >> 3) & 7, k = (int)idx & 7;
   rows[idx] = (k >= j) ? __dmul_rn(falling_factorial(k, j), pow_rounded_once(t[a], k - j)) : 0.0;
 }
 
 // Polynomial.derivative for `count` polynomials of `len` coefficients each:
 // out[c][i] = (i+1) * p[c][i+1], i < len-1   (uav_trajectory.py:25-26)
 __global__ void poly_derivative_kernel(const double* __restrict__ p, int count, int len, double* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= count * (len - 1)) return;
-  const int c = idx / (len - 1), i = idx - c * (len - 1);
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)count * (len - 1)) return;
+  const long long c = idx / (len - 1);
+  const int i = (int)(idx - c * (len - 1));
   out[idx] = __dmul_rn((double)(i + 1), p[c * len + i + 1]);
 }
 
 // Polynomial.pol_coeffs_at_t: out[c][i] = p[c][i] * t[c]**i   (uav_trajectory.py:28-36)
 __global__ void poly_terms_kernel(const double* __restrict__ p, const double* __restrict__ t, int count, int len,
                                   double* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= count * len) return;
-  const int c = idx / len, i = idx - c * len;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)count * len) return;
+  const long long c = idx / len;
+  const int i = (int)(idx - c * len);
   out[idx] = __dmul_rn(p[idx], pow_rounded_once(t[c], i));
 }
 
 int launch_poly_derivative(const double* p, int count, int len, double* out, cudaStream_t stream) {
-  const int total = count * (len - 1);
+  const long long total = (long long)count * (len - 1);
   if (total <= 0) return MST_OK;
-  poly_derivative_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p, count, len, out);
+  poly_derivative_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, count, len, out);
   return check_launch();
 }
 
 int launch_poly_terms(const double* p, const double* t, int count, int len, double* out, cudaStream_t stream) {
-  const int total = count * len;
+  const long long total = (long long)count * len;
   if (total <= 0) return MST_OK;
-  poly_terms_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p, t, count, len, out);
+  poly_terms_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, t, count, len, out);
   return check_launch();
 }
 
@@ -324,8 +329,8 @@ int launch_flat(const double* coef, const double* dur, int B, int n, const doubl
 
 int launch_time_power(const double* t, int count, double* rows, cudaStream_t stream) {
   if (count == 0) return MST_OK;
-  const int total = count * 64;
-  time_power_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t, count, rows);
+  const long long total = (long long)count * 64;
+  time_power_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(t, count, rows);
   return check_launch();
 }
 

@@ -4,7 +4,8 @@
 //
 // Replaces calculate_trajectory1D (src/optimizations/calculatingTrajectories.py:37-197)
 // including its np.linalg.solve (:137).  The row layout follows :65-128 exactly
-//  so pivoting sees the same matrix LAPACK dgesv sees; the band is
+//  so pivoting sees the matrix LAPACK dgesv sees (entries t^k are formed by repeated
+// multiplication here, by libm pow in the reference: equal to a few ulps, not always bitwise); the band is
 // kl = 10 below / ku = 7 above the diagonal (ku = 5 when t[0] == 0, the start rows then
 // being diagonal).  `A` never exists in HBM: it is built from the n durations in shared
 // memory, factorised there, and only the 8 coefficients per piece and axis leave.
@@ -130,6 +131,9 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
       double a[KL + 1];
 #pragma unroll
       for (int r = 0; r <= KL; ++r) a[r] = r <= km ? colj[r] : 0.0;
+      // every lane holds column j in registers before lane 0 swaps and rewrites it below (the CUDA
+      // model does not promise lockstep between the loads above and those stores)
+      __syncwarp();
       int jp = 0;
       double best = fabs(a[0]);
 #pragma unroll

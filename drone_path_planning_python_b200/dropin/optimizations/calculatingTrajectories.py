@@ -86,13 +86,30 @@ def visualize_trajectory3D(pols):
     plt.show()
 
 
-# Module-level smoke fixture with the names, shape and role of the reference's (:240-259): 18
-# rigid-body waypoints (x, y, z, yaw) two seconds apart.  The values here are this package's own — a
-# gentle descending arc through the reference's workspace bounds; the reference's values live in
-# tests/golden/solve_cases.npz (case "reference_test_data"), where the parity tests use them.
+# Module-level fixture of the reference (src/optimizations/calculatingTrajectories.py:240-259): 18
+# rigid-body waypoints (x, y, z, yaw) ``timestep`` seconds apart.  A drop-in exports the reference's
+# VALUES (callers and the golden case "reference_test_data" in tests/golden/solve_cases.npz use them),
+# so the table is kept verbatim.
 timestep = 100/50
-test_data = [[round(-1.0 + 0.08 * i, 6), round(5.0 - 0.14 * i - 0.0004 * i * i, 6), round(1.0 - 0.017 * i, 6),
-              round(0.02 * i, 6)] for i in range(18)]
+test_data = [
+    [-1.0, 5.0, 1.0, 0.0],
+    [-0.9105214656082087, 4.866527813557898, 0.9821609406403813, 0.02039080103534039],
+    [-0.8225743363589189, 4.73288554489947, 0.964441662764501, 0.04077309721300639],
+    [-0.7361272257466368, 4.5990008095166175, 0.946841139664208, 0.06113820463325185],
+    [-0.6511925243577015, 4.464831726680945, 0.9293520786300249, 0.08147761001670759],
+    [-0.5677385453806084, 4.3303072795034305, 0.9119680575644483, 0.10178299225536093],
+    [-0.4857652247831987, 4.19536539455793, 0.8946893929748612, 0.12204500119949559],
+    [-0.40523866600088, 4.05994725771634, 0.8775065705250998, 0.14225598708544368],
+    [-0.3261547497876769, 3.923993481128284, 0.8604168009043632, 0.16240701194973708],
+    [-0.2484752985307498, 3.78743548705188, 0.84341227981323, 0.1824899882345422],
+    [-0.17219220053404993, 3.6502373470789204, 0.8264894614074699, 0.20249698043707148],
+    [-0.09725801527295008, 3.51232995673728, 0.8096428181876703, 0.22241799607297275],
+    [-0.02365621826047004, 3.37365871553904, 0.7928635266349502, 0.24224499181234838],
+    [0.04864606691479989, 3.23417214717458, 0.7761488620638199, 0.2619709834334211],
+    [0.11968750758167002, 3.0938169790745595, 0.75949244060815, 0.2815870183901405],
+    [0.18949994071968002, 2.95253000758626, 0.7428843320283001, 0.3010839819518382],
+    [0.2581249596866899, 2.8102848216266, 0.72632388402931, 0.32045501331803433],
+    [0.32560330474396, 2.667021932848, 0.70980157478244, 0.3396910397023212]]
 
 if __name__ == "__main__":
     traj_points = [Point_time(Waypoint(*row), t=i * timestep) for i, row in enumerate(test_data)]

@@ -18,7 +18,10 @@ class HostPipeline:
     """Preallocated chunked solve+sample+collide over host tensors.
 
     ``run(wp, t, out)`` takes pinned host tensors ``wp[B, n+1, K]`` / ``t[B/G, n+1]`` and
-    fills the pinned host tensors of ``out`` (a ``PipelineResult`` of host tensors)."""
+    fills the pinned host tensors of ``out`` (a ``PipelineResult`` of host tensors).  ``run`` is
+    synchronous for the HOST: it returns after the last device->host copy of every slot has
+    completed (an event per slot), so ``out`` can be read right away.  ``run(..., wait=False)``
+    returns the slot events instead for callers that overlap further work."""
 
     def __init__(self, n: int, K: int, S: int, robot: Mesh, env: Mesh, chunk: int = 65536,
                  share_time_group: int = 1, solver: str = "auto", slots: int = 3, wire: str = "f64"):
@@ -33,12 +36,15 @@ class HostPipeline:
         self.dev = _abi.require_cuda()
         self.n, self.K, self.S, self.G = n, K, S, int(share_time_group)
         self.robot, self.env, self.solver = robot, env, solver
+        if chunk < self.G:
+            raise ValueError("chunk (%d) must hold at least one time-sharing group of %d trajectories" % (chunk, self.G))
         self.chunk = chunk - chunk % self.G
         f64, dev = torch.float64, self.dev
         self.slots = []
         for _ in range(slots):
             self.slots.append({
                 "stream": torch.cuda.Stream(device=dev),
+                "done": torch.cuda.Event(),
                 "wp": torch.empty((self.chunk, n + 1, K), dtype=f64, device=dev),
                 "t": torch.empty((self.chunk // self.G, n + 1), dtype=f64, device=dev),
                 "res": PipelineResult(torch.empty((self.chunk, n, K, 8), dtype=f64, device=dev),
@@ -73,8 +79,10 @@ class HostPipeline:
             d2h = self.n * self.K * 64 + self.n * 8 + 4 + self.S + 1
         return h2d, d2h
 
-    def run(self, wp: torch.Tensor, t: torch.Tensor, out: Optional[PipelineResult] = None) -> PipelineResult:
+    def run(self, wp: torch.Tensor, t: torch.Tensor, out: Optional[PipelineResult] = None, wait: bool = True):
         B = wp.shape[0]
+        if B % self.G != 0 or t.shape[0] != B // self.G:
+            raise ValueError("t must be [B/share_time_group, n+1]")
         if out is None:
             out = self.alloc_host_result(B, self.n, self.K, self.S, self.wire)
         caller = torch.cuda.current_stream()
@@ -101,6 +109,13 @@ class HostPipeline:
                 out.info[b0:b0 + nb].copy_(view.info, non_blocking=True)
                 out.hit[b0:b0 + nb].copy_(view.hit, non_blocking=True)
                 out.any_hit[b0:b0 + nb].copy_(view.any_hit, non_blocking=True)
-        for slot in self.slots:
+                slot["done"].record(st)
+        used = self.slots[:min(len(self.slots), (B + self.chunk - 1) // self.chunk)]
+        for slot in used:
             caller.wait_stream(slot["stream"])
+        if not wait:
+            return out, [slot["done"] for slot in used]
+        # the copies above are asynchronous: order the HOST behind each slot's last device->host copy
+        for slot in used:
+            slot["done"].synchronize()
         return out

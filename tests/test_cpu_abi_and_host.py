@@ -218,51 +218,10 @@ def test_interval_triangle_test_equals_sat_outside_the_touching_band():
 
 
 def _exact_triangles_meet(A, B):
-    """Do two closed, non-degenerate triangles share a point?  Decided in exact rational arithmetic
-    by a method that has nothing in common with a separating-axis test: two triangles meet iff an
-    edge of one meets the other triangle (closed segment against closed triangle; a segment lying
-    in the triangle's plane is handled in 2-D)."""
-    from fractions import Fraction as F
-    A = [[F(float(x)) for x in v] for v in A]
-    B = [[F(float(x)) for x in v] for v in B]
-    sub = lambda a, b: [a[i] - b[i] for i in range(3)]
-    dot = lambda a, b: a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
-    cross = lambda a, b: [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
-
-    def orient2(a, b, c):
-        return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
-
-    def point_in_tri2(p, t):
-        s = [orient2(t[i], t[(i + 1) % 3], p) for i in range(3)]
-        return all(x >= 0 for x in s) or all(x <= 0 for x in s)
-
-    def seg_seg2(p, q, a, b):
-        d1, d2 = orient2(a, b, p), orient2(a, b, q)
-        d3, d4 = orient2(p, q, a), orient2(p, q, b)
-        if d1 == 0 and d2 == 0 and d3 == 0 and d4 == 0:      # collinear: overlap of the ranges
-            k = 0 if p[0] != q[0] or a[0] != b[0] else 1
-            return max(min(p[k], q[k]), min(a[k], b[k])) <= min(max(p[k], q[k]), max(a[k], b[k]))
-        return (d1 * d2 <= 0) and (d3 * d4 <= 0)
-
-    def seg_tri(p, q, t):
-        n = cross(sub(t[1], t[0]), sub(t[2], t[0]))
-        dp, dq = dot(n, sub(p, t[0])), dot(n, sub(q, t[0]))
-        if (dp > 0 and dq > 0) or (dp < 0 and dq < 0):
-            return False
-        if dp == 0 and dq == 0:                               # in the plane: drop the dominant axis
-            k = max(range(3), key=lambda i: abs(n[i]))
-            keep = [i for i in range(3) if i != k]
-            P, Q = [p[i] for i in keep], [q[i] for i in keep]
-            T = [[v[i] for i in keep] for v in t]
-            return (point_in_tri2(P, T) or point_in_tri2(Q, T) or
-                    any(seg_seg2(P, Q, T[i], T[(i + 1) % 3]) for i in range(3)))
-        s = dp / (dp - dq)
-        x = [p[i] + s * (q[i] - p[i]) for i in range(3)]
-        side = [dot(cross(sub(t[(i + 1) % 3], t[i]), sub(x, t[i])), n) for i in range(3)]
-        return all(v >= 0 for v in side)
-
-    return (any(seg_tri(A[i], A[(i + 1) % 3], B) for i in range(3)) or
-            any(seg_tri(B[i], B[(i + 1) % 3], A) for i in range(3)))
+    """Exact rational-arithmetic decision (oracle/exact_geometry.py): an edge of one triangle meets
+    the other closed triangle — nothing in common with a separating-axis test."""
+    from oracle import exact_geometry as xg
+    return xg.triangles_meet(A, B)
 
 
 def test_sat_restatement_decides_exactly_whether_lattice_triangles_meet():
@@ -294,3 +253,52 @@ def test_sat_restatement_decides_exactly_whether_lattice_triangles_meet():
     still = np.zeros((1, 4))
     c_says = np.array([build_oracle.c_collide_poses(t[0][None], t[1][None], still)[0] for t in tri[:400]])
     assert np.array_equal(c_says.astype(bool), want[:400])    # the C restatement, one-triangle meshes
+
+
+def _anchors(golden_dir):
+    with np.load(os.path.join(golden_dir, "collision_anchors.npz")) as z:
+        data = {k: z[k] for k in z.files}
+    pairs = []
+    for i in range(4):
+        key = "pair%d" % i
+        pairs.append({f: data[key + "__" + f] for f in ("robot", "env", "poses", "kind", "exact", "margin")})
+    return pairs
+
+
+def test_mesh_level_collision_anchors_hold_for_both_restatements(golden_dir):
+    """Robot-pose-vs-environment answers decided in exact rational arithmetic on the shipped mesh
+    pairs (oracle/make_collision_anchors.py; what fcl.collide decides at fcl_checker.py:93-100),
+    including the one pose the reference itself evaluates (fcl_checker.py:124-136).  A subset is
+    re-derived here; the numpy and C restatements and the kernels' culled host routine must
+    reproduce EVERY stored answer (poses are lattice / exact half turns / shared corners, so no
+    epsilon band is needed)."""
+    from drone_path_planning_python_b200 import meshio
+    from oracle import build_oracle, collision_oracle as co, exact_geometry as xg
+    lib = _hostcheck()
+    seen_reference_pose = False
+    for pair in _anchors(golden_dir):
+        robot = co.mesh_triangles(meshio.shipped_mesh(str(pair["robot"])))
+        env = co.mesh_triangles(meshio.shipped_mesh(str(pair["env"])))
+        poses, exact, kind = pair["poses"], pair["exact"], pair["kind"]
+        R, T = co.pose_matrices(poses)
+        pick = np.concatenate([np.arange(0, len(poses), 9), np.flatnonzero(kind == 2)])
+        for i in pick:
+            assert int(xg.robot_meets_env(robot, env, R[i], T[i])) == exact[i], (str(pair["env"]), i)
+        assert (exact[kind == 1] == 1).all()                          # a shared corner is a collision
+        assert 0.2 < exact.mean() < 0.8
+        flags = co.collide_poses(robot, env, poses)
+        assert np.array_equal(flags, exact), str(pair["env"])
+        assert np.array_equal(build_oracle.c_collide_poses(robot, env, poses), exact)
+        Rc, Tc = np.ascontiguousarray(R.reshape(-1, 9)), np.ascontiguousarray(T)
+        rt, et = np.ascontiguousarray(robot.reshape(-1, 9)), np.ascontiguousarray(env.reshape(-1, 9))
+        out = np.zeros(len(poses), np.uint8)
+        rc = lib.hostcheck_collide_culled(P(rt.ctypes.data), len(robot), P(et.ctypes.data), len(env), P(Rc.ctypes.data),
+                                          P(Tc.ctypes.data), len(poses), 1, 0, P(out.ctypes.data))
+        assert rc >= 0 and np.array_equal(out, exact), str(pair["env"])
+        if (kind == 2).any():
+            i = int(np.flatnonzero(kind == 2)[0])
+            # fcl_checker.py:133-136: robot-scene-triangle at [-1.21917, -0.441611, -0.0462389] is metres
+            # away from the wall at y = 3.9 .. 4.1: free (the reference prints 0 for it)
+            assert exact[i] == 0 and pair["margin"][i] > 1.0
+            seen_reference_pose = True
+    assert seen_reference_pose

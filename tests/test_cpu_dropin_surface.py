@@ -1,6 +1,7 @@
 """CPU tier: the drop-in packages expose the reference's module surface and import
 without ROS / OMPL / FCL / matplotlib.  Numbers need the GPU (tests/test_gpu_dropin.py)."""
 import importlib
+import os
 import sys
 
 import numpy as np
@@ -12,11 +13,11 @@ def dropin():
     import drone_path_planning_python_b200 as mst
     path = mst.dropin_path()
     sys.path.insert(0, path)
-    for name in [m for m in sys.modules if m.split(".")[0] in ("optimizations", "RigidBodyPlanners", "scripts")]:
+    for name in [m for m in sys.modules if m.split(".")[0] in ("optimizations", "RigidBodyPlanners", "scripts", "trajectory_visualising")]:
         del sys.modules[name]
     yield path
     sys.path.remove(path)
-    for name in [m for m in sys.modules if m.split(".")[0] in ("optimizations", "RigidBodyPlanners", "scripts")]:
+    for name in [m for m in sys.modules if m.split(".")[0] in ("optimizations", "RigidBodyPlanners", "scripts", "trajectory_visualising")]:
         del sys.modules[name]
 
 
@@ -30,6 +31,24 @@ def test_optimizations_star_import_surface(dropin):
     for name in ("calculate_trajectory1D", "calculate_trajectory4D", "visualize_trajectory3D", "test_data", "timestep"):
         assert hasattr(ct, name), name
     assert len(ct.test_data) == 18 and ct.timestep == 2.0
+    # the reference's own values (calculatingTrajectories.py:240-259), stored by oracle/make_golden.py
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solve_cases.npz"))
+    assert np.array_equal(np.asarray(ct.test_data, dtype=np.float64), gold["reference_test_data__wp"])
+
+
+def test_trajectory_visualising_surface(dropin):
+    """src/trajectory_visualising/__init__.py:1-2 and visualization.py's public names."""
+    tv = importlib.import_module("trajectory_visualising")
+    for name in ("Trajectory", "TrajectoryOutput", "get_nav_path_msg"):
+        assert hasattr(tv, name), name
+    vis = importlib.import_module("trajectory_visualising.visualization")
+    for name in ("visualize_python", "get_nav_path_msg", "Trajectory", "TrajectoryOutput", "Polynomial4D", "np"):
+        assert hasattr(vis, name), name
+    ut = importlib.import_module("trajectory_visualising.uav_trajectory")
+    for name in ("normalize", "Polynomial", "TrajectoryOutput", "Polynomial4D", "Trajectory"):
+        assert hasattr(ut, name), name
+    tr = tv.Trajectory()
+    assert tr.polynomials is None and tr.duration is None
 
 
 def test_plain_records_behave_like_the_reference(dropin, capsys):

@@ -17,7 +17,7 @@ def dropin():
     sys.path.insert(0, path)
     yield path
     sys.path.remove(path)
-    for name in [m for m in sys.modules if m.split(".")[0] in ("optimizations", "RigidBodyPlanners", "scripts")]:
+    for name in [m for m in sys.modules if m.split(".")[0] in ("optimizations", "RigidBodyPlanners", "scripts", "trajectory_visualising")]:
         del sys.modules[name]
 
 
@@ -111,6 +111,40 @@ def test_trajectory_loadcsv_and_eval(dropin, golden_dir, tmp_path):
     assert one.pos.shape == (3,) and one.acc.shape == (3,)
     with pytest.raises(AssertionError):
         tr.eval(-0.1)
+
+
+def test_trajectory_visualising_nav_path(dropin, golden_dir, tmp_path):
+    """get_nav_path_msg (src/trajectory_visualising/visualization.py:39-71) on the reference's own
+    src/traj.csv: one pose per np.arange(0, duration, timestep) sample, position = Trajectory.eval(t).pos
+    + offset, orientation = quaternion_from_euler(0, 0, -yaw) — against the unmodified reference's
+    Trajectory.eval outputs stored in tests/golden/trajectory_eval.npz."""
+    import math
+    import trajectory_visualising as tv
+    from trajectory_visualising import visualization
+    z = _load(golden_dir, "trajectory_eval.npz")
+    path = tmp_path / "traj.csv"
+    np.savetxt(str(path), z["traj__file_rows"], delimiter=",", header="duration,x^0,...", comments="")
+    tr = tv.Trajectory()
+    tr.loadcsv(str(path))
+    assert isinstance(tr.eval(0.0), tv.TrajectoryOutput)
+    offset = [0.25, -1.0, 0.5]
+    msg = tv.get_nav_path_msg(tr, 0.1, offset)
+    ts = np.arange(0, tr.duration, 0.1)
+    assert np.array_equal(ts, z["traj__t"][:-1]) and len(msg.poses) == len(ts)
+    assert msg.header.frame_id == "world"
+    for s, pose in enumerate(msg.poses):
+        want = z["traj__pos"][s] + np.asarray(offset)
+        got = np.array([pose.pose.position.x, pose.pose.position.y, pose.pose.position.z])
+        assert np.array_equal(got, want), s                                   # bit-exact positions
+        yaw = float(z["traj__yaw"][s])
+        assert pose.pose.orientation.x == 0.0 and pose.pose.orientation.y == 0.0
+        assert pose.pose.orientation.z == math.sin(-yaw / 2.0) and pose.pose.orientation.w == math.cos(-yaw / 2.0)
+    # skiprows=1 quirk through this package too: a header-less polynomial matrix loses its first piece
+    np.savetxt(str(path), z["pol1__file_rows"], delimiter=",")
+    tr.loadcsv(str(path))
+    assert tr.n_pieces() == int(z["pol1__n_pieces"]) == len(z["pol1__file_rows"]) - 1
+    pos, quat = visualization.sample_path(tr, 0.1)
+    assert np.array_equal(pos, z["pol1__pos"][:len(pos)])
 
 
 def test_fcl_checker_dropin(dropin, tmp_path):

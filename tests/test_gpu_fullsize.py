@@ -195,13 +195,21 @@ def test_config5_pipeline_one_million():
     assert torch.equal(hit, res.hit[sl])
     again = mst.pipeline(wp, t, S, robot, env)
     assert torch.equal(again.hit, res.hit) and torch.equal(again.coef, res.coef)     # deterministic
-    hits = res.hit.cpu().numpy()
-    for b in (0, 777777, B - 1):
-        coef, dur = mo.solve_waypoints(wp[b], t[b])
-        got = res.coef[b].cpu().numpy()
-        assert (np.abs(got - coef).max(axis=(0, 2)) / np.abs(coef).max(axis=(0, 2))).max() <= 1e-9
-        ts = mo.uniform_sample_times(dur, S)
-        p = mo.sample_trajectory(coef, dur, ts)
-        ref, margin = co.collide_poses(robot_tris, env_tris, np.concatenate([p, np.zeros((S, 1))], 1), with_margin=True)
-        clear = np.abs(margin) > 1e-7
-        assert np.array_equal(hits[b][clear], ref[clear])
+    # ---- the oracle on 4,096 trajectories spread over the batch (process pool; C collision restatement)
+    from _oracle_pool import oracle_pipeline
+    pick = np.unique(np.concatenate([[0, 777777, B - 1], rng.choice(B, 4096, replace=False)]))
+    ref_coef, ref_pos, ref_hit = oracle_pipeline(wp[pick], t[pick], S, robot_tris, env_tris)
+    got = res.coef[torch.as_tensor(pick, device=res.coef.device)].cpu().numpy()
+    err = np.abs(got - ref_coef).max(axis=(1, 3)) / np.abs(ref_coef).max(axis=(1, 3))      # per trajectory and axis
+    assert err.max() <= 1e-9, err.max()
+    hits = res.hit[torch.as_tensor(pick, device=res.hit.device)].cpu().numpy()
+    differ = np.argwhere(hits != ref_hit)
+    # flags are exact except for samples within EPS of touching (north star): the few that differ
+    # must sit inside the band, measured with the numpy restatement's margin
+    assert len(differ) <= 1e-4 * hits.size, len(differ)
+    for q, s_ in differ:
+        pose = np.concatenate([ref_pos[q, s_, :3], [0.0]])[None]
+        _, margin = co.collide_poses(robot_tris, env_tris, pose, with_margin=True)
+        assert abs(margin[0]) <= 1e-7, (int(pick[q]), int(s_), float(margin[0]))
+    print("config 5: %d trajectories vs the oracle, worst coefficient error %.2e, %d of %d flags inside the band"
+          % (len(pick), err.max(), len(differ), hits.size))
