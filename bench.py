@@ -11,8 +11,11 @@ robot `custom_triangle_robot` vs obstacle `env-scene-ltu-experiment`, seed 20261
 §8d).  Inputs + outputs are ~2.4 GB per step, far larger than the 126 MB L2.
 
 Multi-GPU (torchrun, one process per GPU): trajectories are sharded by index, every rank
-runs the same per-GPU batch (weak scaling), and the final coefficients and collision flags
-are all-gathered over NCCL, chunk by chunk, overlapped with the next chunk's kernels.
+runs the same per-GPU batch (weak scaling), and the results are all-gathered over NVLink: by
+default what the reference produces — path_to_pol's float32 polynomial matrix + the collision
+flags — stored to every peer's buffer from inside the single-pass kernel (peer stores); the
+FP64-coefficient gather (copy-engine push) and the flags-only gather are timed beside it, plus
+the strong-scaling reading of configs[4] (1 M trajectories in total).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
 """
@@ -64,27 +67,43 @@ def mesh_soups():
 
 
 # --------------------------------------------------------------------------- CPU arm
+# The reference's own CPU implementation of the path: the UNMODIFIED package
+# src/optimizations of the reference (placed under the git-ignored oracle/_ref/ by
+# __graft_entry__.build(), oracle/build_oracle.populate_ref) — calculate_trajectory1D per axis
+# (calculatingTrajectories.py:37-197) and PiecewisePolynomial.eval per sample and axis
+# (uav_trajectory.py:154-169) — plus the C restatement of the collision test (python-fcl is not
+# installable here).  If oracle/_ref is absent the oracle port is timed instead and the
+# line says kind = "port".
 _CPU_STATE = {}
 
 
 def _cpu_init():
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    from oracle import build_oracle  # noqa: F401
+    from oracle import build_oracle
     _CPU_STATE["soups"] = mesh_soups()
+    _CPU_STATE["ref"] = build_oracle.import_ref()
 
 
 def _cpu_work(args):
-    """Reference algorithm for a slice of trajectories: per-axis dense assembly + solve,
-    Python Horner sampling (oracle/minsnap_oracle.py), C SAT collision (oracle/collision_oracle.c)."""
     from oracle import build_oracle, minsnap_oracle as mo
     wp, t = args
     robot, env = _CPU_STATE["soups"]
+    ref = _CPU_STATE["ref"]
     hits = 0
     for b in range(wp.shape[0]):
-        coef, dur = mo.solve_waypoints(wp[b], t[b])
-        ts = mo.uniform_sample_times(dur, S_SAMPLES)
-        pos = mo.sample_trajectory(coef, dur, ts)
+        if ref is not None:
+            opt, ct = ref
+            pts = [opt.Point_time(opt.Waypoint(float(wp[b, i, 0]), float(wp[b, i, 1]), float(wp[b, i, 2]), 0.0),
+                                  t=float(t[b, i])) for i in range(wp.shape[1])]
+            totals = [ct.calculate_trajectory1D(pts, k)[1] for k in range(K_AX)]
+            dt = sum(totals[0].time_durations) / S_SAMPLES
+            pos = np.array([[float(np.asarray(tot.eval(s * dt)).reshape(())) for tot in totals]
+                            for s in range(S_SAMPLES)])
+        else:
+            coef, dur = mo.solve_waypoints(wp[b], t[b])
+            ts = mo.uniform_sample_times(dur, S_SAMPLES)
+            pos = mo.sample_trajectory(coef, dur, ts)
         poses = np.concatenate([pos, np.zeros((S_SAMPLES, 1))], axis=1)
         hits += int(build_oracle.c_collide_poses(robot, env, poses).any())
     return hits
@@ -95,6 +114,11 @@ def host_cores():
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def cpu_kind():
+    return "reference" if os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "optimizations", "calculatingTrajectories.py")) \
+        else "port"
 
 
 class CpuArm:
@@ -116,12 +140,35 @@ class CpuArm:
         self.pool.join()
 
 
+def cpu_baseline(wp_np, t_np, per_core):
+    """All-core and one-core figures of the CPU arm on the first trajectories of the batch."""
+    cores = host_cores()
+    kind = cpu_kind()
+    nsamp = per_core * cores
+    arm = CpuArm(cores)
+    arm.run(wp_np[:cores], t_np[:cores])
+    secs = arm.run(wp_np[:nsamp], t_np[:nsamp])
+    arm.close()
+    one = CpuArm(1)
+    one.run(wp_np[:1], t_np[:1])
+    n1 = max(4, per_core)
+    secs1 = one.run(wp_np[:n1], t_np[:n1])
+    one.close()
+    what = ("unmodified reference package (oracle/_ref/optimizations: calculate_trajectory1D x %d axes, "
+            "PiecewisePolynomial.eval x %d samples) + C restatement of the collision test" % (K_AX, S_SAMPLES)) \
+        if kind == "reference" else "oracle port (numpy restatement) + C restatement of the collision test"
+    return {"value": nsamp / secs, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "first %d trajectories of the same batch, %.1f s wall on %d processes; %s"
+                      % (nsamp, secs, cores, what),
+            "one_core": {"value": n1 / secs1, "cores": 1, "sample": "first %d trajectories, %.1f s" % (n1, secs1)}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    per_step = 16 * cores
+    per_step = 8 * cores
     wp, t = make_workload(per_step * (args.steps + args.warmup), SEED)
     arm = CpuArm(cores)
     for w in range(args.warmup):
@@ -133,7 +180,10 @@ def run_reference(args):
         elapsed += arm.run(wp[sl], t[sl])
     arm.close()
     value = per_step * args.steps / elapsed
-    sample = "%d trajectories per step (16 per core) of the same generator" % per_step
+    kind = cpu_kind()
+    sample = "%d trajectories per step (8 per core) of the same generator; %s" % (
+        per_step, "unmodified reference package from oracle/_ref + C collision restatement" if kind == "reference"
+        else "oracle port + C collision restatement")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
@@ -141,7 +191,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[4] shape: %d pieces x %d axes, S=%d, %s vs %s; bounded sample"
                                % (N_SEG, K_AX, S_SAMPLES, ROBOT, ENV), "trajectories_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -190,6 +240,17 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def load_profile_counters():
+    """Per-trajectory counters of the dominant kernel from the tracked ncu capture
+    (profiles/r2_onepass_counters.json, written by tools/ncu_summary.py from the .ncu-rep of this
+    same command): DRAM bytes and executed FP64 instructions.  None when the file is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_onepass_counters.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -222,50 +283,13 @@ def run_ours(args):
     wp = wp_host.to(dev)
     t = t_host.to(dev)
 
-    res = mst.PipelineResult(torch.empty((B, N_SEG, K_AX, 8), dtype=torch.float64, device=dev),
-                             torch.empty((B, N_SEG), dtype=torch.float64, device=dev),
-                             torch.empty((B,), dtype=torch.int32, device=dev),
-                             torch.empty((B, S_SAMPLES), dtype=torch.uint8, device=dev),
-                             torch.empty((B,), dtype=torch.uint8, device=dev))
-
-    # multi-GPU: all-gather of coefficients + flags, chunked and overlapped with the next chunk.
-    # Preferred: peer push over NVLink with the copy engines (distributed.PeerPushAllGather);
-    # fallback: NCCL all_gather_into_tensor (distributed.ChunkedAllGather).
-    from drone_path_planning_python_b200.distributed import ChunkedAllGather, PeerPushAllGather
-    gather, gather_kind, n_chunks = None, None, 1
-    if args.gather_chunks <= 0:
-        args.gather_chunks = 4 if world <= 4 else 2
-    if world > 1:
-        if args.gather == "push":
-            try:
-                gather = PeerPushAllGather(B, world, rank, args.gather_chunks, [res.coef, res.hit, res.any_hit],
-                                           streams=args.push_streams)
-                gather_kind = "peer push over NVLink (copy engines, symmetric memory)"
-                res = mst.PipelineResult(gather.local_slot(0), res.dur, res.info, gather.local_slot(1),
-                                         gather.local_slot(2))
-            except Exception as exc:  # symmetric memory unavailable on this box
-                sys.stderr.write("peer-push gather unavailable (%r); using NCCL\n" % (exc,))
-                gather = None
-        if gather is None:
-            gather = ChunkedAllGather(B, world, args.gather_chunks, [res.coef, res.hit, res.any_hit])
-            gather_kind = "NCCL all_gather_into_tensor"
-        n_chunks = len(gather.plan)
-
-    def chunk_view(lo, hi):
-        return mst.PipelineResult(res.coef[lo:hi], res.dur[lo:hi], res.info[lo:hi], res.hit[lo:hi], res.any_hit[lo:hi])
-
-    def compute_chunk(lo, hi):
-        view = chunk_view(lo, hi)
-        mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
-        return view.coef, view.hit, view.any_hit
-
-    def step():
-        if world == 1:
-            mst.pipeline(wp, t, S_SAMPLES, robot, env, out=res)
-        elif isinstance(gather, PeerPushAllGather):
-            gather.run(compute_chunk)
-        else:
-            gather.run(compute_chunk, assemble=False)   # results stay in [chunk][rank][...] staging buffers
+    def new_result(count):
+        return mst.PipelineResult(torch.empty((count, N_SEG, K_AX, 8), dtype=torch.float64, device=dev),
+                                  torch.empty((count, N_SEG), dtype=torch.float64, device=dev),
+                                  torch.empty((count,), dtype=torch.int32, device=dev),
+                                  torch.empty((count, S_SAMPLES), dtype=torch.uint8, device=dev),
+                                  torch.empty((count,), dtype=torch.uint8, device=dev))
+    res = new_result(B)
 
     def barrier():
         if world > 1:
@@ -285,6 +309,41 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- multi-GPU data planes: what is gathered, and how -------------------------------
+    # default "f32-wire": the float32 polynomial matrix the reference's path_to_pol emits + the flags,
+    # stored to every peer's buffer from INSIDE the single-pass kernel (NVLink peer stores);
+    # "flags-only": flags alone, same mechanism; "f64-full": FP64 coefficients + flags pushed by the
+    # copy engines chunk by chunk (round 1's data plane).
+    from drone_path_planning_python_b200.distributed import PeerPushAllGather, PeerStoreGather
+    gathers, gather_note = {}, None
+    if world > 1:
+        gathers["f32-wire"] = PeerStoreGather(B, world, rank, N_SEG, K_AX, S_SAMPLES, dev, mode="pol_matrix_f32")
+        gathers["flags-only"] = PeerStoreGather(B, world, rank, N_SEG, K_AX, S_SAMPLES, dev, mode="flags")
+        if args.gather_chunks <= 0:
+            args.gather_chunks = 4 if world <= 4 else 2
+        gathers["f64-full"] = PeerPushAllGather(B, world, rank, args.gather_chunks, [res.coef, res.hit, res.any_hit],
+                                                streams=args.push_streams)
+        gather_note = ("%s: in-kernel NVLink peer stores of path_to_pol's float32 matrix + flags (mst_pipeline_wire, "
+                       "symmetric memory)" % args.gather)
+
+    push = gathers.get("f64-full")
+    push_res = None if push is None else mst.PipelineResult(push.local_slot(0), res.dur, res.info, push.local_slot(1),
+                                                            push.local_slot(2))
+
+    def push_chunk(lo, hi):
+        view = mst.PipelineResult(push_res.coef[lo:hi], push_res.dur[lo:hi], push_res.info[lo:hi], push_res.hit[lo:hi],
+                                  push_res.any_hit[lo:hi])
+        mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
+
+    def make_step(mode):
+        if world == 1:
+            return lambda: mst.pipeline(wp, t, S_SAMPLES, robot, env, out=res)
+        if mode == "f64-full":
+            return lambda: push.run(push_chunk)
+        g = gathers[mode]
+        return lambda: g.run(lambda wire: mst.pipeline_wire(wp, t, S_SAMPLES, robot, env, wire, out=res))
+
+    step = make_step(args.gather)
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
@@ -296,10 +355,65 @@ def run_ours(args):
     bad = int((res.info != 0).sum().item())
     hit_rate = float(res.any_hit.float().mean().item())
 
-    # --- the two kernels of the step alone, timed live with CUDA events on the launching stream
+    # ---- N > 1: the other gather modes, strong scaling, and a check of the gathered data -------------
+    scaling_modes, strong, gather_ok = None, None, None
+    if world > 1:
+        side_steps = max(3, args.steps // 4)
+        scaling_modes = {}
+        for mode in ("f64-full", "f32-wire", "flags-only"):
+            if mode == args.gather:
+                ms = ms_per_step
+            else:
+                fn = make_step(mode)
+                for _ in range(2):
+                    fn()
+                ms = timed(fn, side_steps) / side_steps
+            per_traj = (N_SEG * K_AX * 64 + S_SAMPLES + 1) if mode == "f64-full" else \
+                gathers[mode].bytes_per_trajectory(N_SEG, K_AX, S_SAMPLES)
+            scaling_modes[mode] = {"ms_per_step": ms, "value": world * B / (ms * 1e-3),
+                                   "gathered_bytes_per_trajectory": per_traj,
+                                   "nvlink_in_gbs_per_gpu": (world - 1) * B * per_traj / (ms * 1e-3) / 1e9}
+        # out of the timed region: every rank's slot of this rank's gathered buffers must hold that
+        # rank's results (checksums of the local results, exchanged with NCCL)
+        g = gathers["f32-wire"]
+        g.run(lambda wire: mst.pipeline_wire(wp, t, S_SAMPLES, robot, env, wire, out=res))
+        torch.cuda.synchronize()
+
+        def sums(mat, hit, any_hit):
+            return torch.stack([mat.view(torch.int32).to(torch.int64).sum(), hit.to(torch.int64).sum(),
+                                (hit.to(torch.int64) * torch.arange(1, S_SAMPLES + 1, device=dev)).sum(),
+                                any_hit.to(torch.int64).sum()])
+        mine = sums(mst.pack_pol_matrix(res.coef, res.dur), res.hit, res.any_hit)
+        allsums = torch.empty((world, 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allsums, mine.view(1, 4))
+        gather_ok = True
+        for r in range(world):
+            sl = slice(r * B, (r + 1) * B)
+            got = sums(g.buffers["pol_matrix"][sl], g.buffers["hit"][sl], g.buffers["any_hit"][sl])
+            gather_ok = gather_ok and bool(torch.equal(got, allsums[r]))
+        flag = torch.tensor([0 if gather_ok else 1], device=dev)
+        dist.all_reduce(flag)
+        gather_ok = int(flag.item()) == 0
+        # strong scaling of configs[4]: 1,048,576 trajectories in total, sharded over the ranks
+        Bs = TRAJ_PER_GPU // world
+        gs = PeerStoreGather(Bs, world, rank, N_SEG, K_AX, S_SAMPLES, dev, mode="pol_matrix_f32")
+        res_s = new_result(Bs)
+        fn = lambda: gs.run(lambda wire: mst.pipeline_wire(wp[:Bs], t[:Bs], S_SAMPLES, robot, env, wire, out=res_s))
+        for _ in range(3):
+            fn()
+        ms = timed(fn, args.steps) / args.steps
+        strong = {"total_trajectories": Bs * world, "ms_per_step": ms, "value": Bs * world / (ms * 1e-3),
+                  "gather": "f32-wire"}
+
+    # ---- the kernels of the step alone, timed live with CUDA events on the launching stream -----------
     stage_ms = {}
-    ws = torch.empty((max(1, lib.mst_solve_workspace_bytes(B, N_SEG, K_AX, 1)),), dtype=torch.uint8, device=dev)
+    ws = torch.empty((max(1, lib.mst_pipeline_workspace_bytes(B, N_SEG, K_AX, 1, S_SAMPLES)),), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
+
+    def pipeline_only():
+        _abi.check(lib.mst_pipeline(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES, robot.handle,
+                                    env.handle, res.coef.data_ptr(), res.dur.data_ptr(), res.info.data_ptr(),
+                                    res.hit.data_ptr(), res.any_hit.data_ptr(), ws.data_ptr(), st), "mst_pipeline")
 
     def solve_only():
         _abi.check(lib.mst_solve_batch(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO,
@@ -310,9 +424,11 @@ def run_ours(args):
         _abi.check(lib.mst_collide_trajectories(res.coef.data_ptr(), res.dur.data_ptr(), B, N_SEG, K_AX, S_SAMPLES,
                                                 robot.handle, env.handle, res.hit.data_ptr(), res.any_hit.data_ptr(),
                                                 st), "mst_collide_trajectories")
-    solve_only(); collide_only()
-    stage_ms["condensed_kernel (+ banded_lu_kernel on the declined list)"] = timed(solve_only, args.steps) / args.steps
-    stage_ms["sample_collide_kernel"] = timed(collide_only, args.steps) / args.steps
+    pipeline_only(); solve_only(); collide_only()
+    side = max(3, args.steps // 2)
+    stage_ms["onepass_kernel (+ list-mode banded_lu / sample_collide, empty list)"] = timed(pipeline_only, side) / side
+    stage_ms["two-launch reference: condensed_cols_kernel"] = timed(solve_only, side) / side
+    stage_ms["two-launch reference: sample_collide_kernel"] = timed(collide_only, side) / side
 
     peaks = {}
     try:
@@ -322,16 +438,38 @@ def run_ours(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # dominant kernel: sample_collide_kernel.  Its compulsory bytes per trajectory: coefficients
-    # and durations in, per-sample flags + any-flag out.
-    dom_ms = stage_ms["sample_collide_kernel"]
-    dom_bytes = N_SEG * K_AX * 64 + N_SEG * 8 + S_SAMPLES + 1
-    achieved = B * dom_bytes / (dom_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/ (ncu --set full,
-    # 262,144 trajectories per launch, cold L2), scaled to this launch's trajectory count
-    traffic_per_traj = (541.113344e6 + 30.006528e6) / 262144
+    # dominant kernel: onepass_kernel = the whole step.  Compulsory bytes per trajectory:
+    # waypoints + stamps in, coefficients + flags out = ALG_BYTES.
+    dom_ms = stage_ms["onepass_kernel (+ list-mode banded_lu / sample_collide, empty list)"]
+    achieved = B * ALG_BYTES / (dom_ms * 1e-3) / 1e9
+    counters = load_profile_counters()
+    traffic = counters["dram_bytes_per_trajectory"] * B if counters else None
+    # FP64 roof: measured in this run (tools/fp64_peak.py)
+    fp64 = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import fp64_peak
+        fp64 = fp64_peak.measure()
+    except Exception as exc:  # the probe library did not travel
+        sys.stderr.write("fp64 peak probe unavailable: %r\n" % (exc,))
+    traj_per_s = B / (dom_ms * 1e-3)
+    fp64_block = None
+    if fp64:
+        peak_tf = fp64["fp64_fma_tflops"]
+        fp64_block = {"fp64_peak_tflops": peak_tf, "fp64_peak_source": "measured", "fp64_peak_how": fp64["how"],
+                      "fp64_mul_add_tflops": fp64["fp64_mul_add_tflops"], "sm_mhz_after_probe": fp64.get("sm_mhz_after"),
+                      # SURVEY §8d's credited flops (banded-LU formulation of the reference's own system)
+                      "credited_flops_per_trajectory": 45600,
+                      "fp64_frac_credited": traj_per_s * 45600 / (peak_tf * 1e12)}
+        if counters and counters.get("fp64_flops_per_trajectory"):
+            ex = counters["fp64_flops_per_trajectory"]
+            fp64_block.update({"executed_flops_per_trajectory": ex, "fp64_frac": traj_per_s * ex / (peak_tf * 1e12),
+                               "executed_fp64_instructions_per_trajectory": counters.get("fp64_instructions_per_trajectory"),
+                               "fp64_pipe_frac": (traj_per_s * counters["fp64_instructions_per_trajectory"] /
+                                                  fp64["fma"]["thread_instructions_per_s"])
+                               if counters.get("fp64_instructions_per_trajectory") else None})
 
-    # --- end to end through HOST buffers (pinned), copies inside the timed region ----------
+    # ---- end to end through HOST buffers (pinned), copies inside the timed region ----------
     hp = HostPipeline(N_SEG, K_AX, S_SAMPLES, robot, env, chunk=args.e2e_chunk)
     host_out = HostPipeline.alloc_host_result(B, N_SEG, K_AX, S_SAMPLES)
 
@@ -355,6 +493,19 @@ def run_ours(args):
     e2e32_ms = timed(e2e32_step, e2e_steps) / e2e_steps
     h2d32, d2h32 = hp32.bytes_per_trajectory()
 
+    launches_per_step = lib.mst_pipeline_launch_count(B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES)
+    if world > 1:
+        launches_per_step += 1      # wire patch kernel (list mode) behind mst_pipeline_wire
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "hbm_frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "onepass_kernel<3> (the whole step: solve + sample + collide in one launch)",
+                "alg_bytes_per_trajectory": ALG_BYTES, "trajectories_per_launch": B, "kernel_ms": dom_ms,
+                "kernels_ms": stage_ms,
+                "traffic_source": "profiles/r2_onepass_counters.json (ncu --set full of this command)" if counters else None,
+                "note": "instruction/latency bound (branchy FP64 geometry, short recurrences), not bandwidth bound: "
+                        "both fractions are reported, see profiles/"}
+    if fp64_block:
+        roofline.update(fp64_block)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -364,39 +515,26 @@ def run_ours(args):
                                % (B, N_SEG, K_AX, S_SAMPLES, ROBOT, ENV, SEED),
                    "trajectories_per_gpu": B, "l2": "inputs+outputs %.2f GB per step >> 126 MB L2 (no flush needed)"
                    % (B * (ALG_BYTES + N_SEG * 8 + 4) / 1e9),
-                   "gather": None if world == 1 else "%s of coef(f64)+hit+any_hit, %d chunks" % (gather_kind, n_chunks),
-                   "solver": "auto (condensed LDL^T; banded pivoted LU for wide duration spreads)"},
+                   "gather": gather_note,
+                   "solver": "auto (condensed LDL^T inside the single-pass kernel; banded pivoted LU for wide duration spreads)"},
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
-                "chunk": args.e2e_chunk, "note": "pinned host in/out (FP64 coefficients), 3-slot copy/compute overlap; "
-                "PCIe-bound by the device->host copy",
+                "chunk": args.e2e_chunk, "note": "pinned host in/out (FP64 coefficients), 3-slot copy/compute overlap, "
+                "host waits for the last device->host copy; PCIe-bound by the device->host copy",
                 "pol_matrix_f32_wire": {"value": world * B / (e2e32_ms * 1e-3), "ms_per_step": e2e32_ms,
                                         "d2h_bytes_per_step": int(d2h32 * B),
                                         "note": "same call returning path_to_pol's float32 (n,33)-style matrix"}},
-        "gpu_launches": args.steps * n_chunks * lib.mst_pipeline_launch_count(B // n_chunks, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": traffic_per_traj * B,
-                     "peak_source": peak_src, "kernel": "sample_collide_kernel<3> (%.0f %% of the step)"
-                     % (100 * dom_ms / ms_per_step if world == 1 else 100 * dom_ms / sum(stage_ms.values())),
-                     "alg_bytes_per_trajectory": dom_bytes, "trajectories_per_launch": B,
-                     "kernel_ms": dom_ms, "kernels_ms": stage_ms,
-                     "whole_step": {"alg_bytes_per_trajectory": ALG_BYTES,
-                                    "achieved_gbs": (B * ALG_BYTES / (ms_per_step * 1e-3) / 1e9) if world == 1 else None},
-                     "note": "instruction/latency bound (branchy FP64 geometry), not bandwidth bound: see profiles/"},
-        "checks": {"solver_failures": bad, "any_hit_rate": hit_rate},
+        "gpu_launches": args.steps * launches_per_step,
+        "roofline": roofline,
+        "checks": {"solver_failures": bad, "any_hit_rate": hit_rate, "gathered_buffers_verified": gather_ok},
     }
+    if scaling_modes:
+        line["gather_modes"] = scaling_modes
+        line["strong_scaling"] = strong
 
     if world == 1 and not args.no_cpu_baseline:
-        cores = host_cores()
-        nsamp = 256 * cores if not args.quick else 16 * cores
-        arm = CpuArm(cores)
-        arm.run(wp_np[:cores], t_np[:cores])
-        secs = arm.run(wp_np[:nsamp], t_np[:nsamp])
-        arm.close()
-        line["cpu_baseline"] = {"value": nsamp / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "first %d trajectories of the same batch, %.1f s wall on %d processes"
-                                          % (nsamp, secs, cores)}
+        line["cpu_baseline"] = cpu_baseline(wp_np, t_np, 4 if args.quick else 32)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -413,7 +551,8 @@ def main():
     ap.add_argument("--gather-chunks", type=int, default=0,
                     help="chunks of the overlapped all-gather (0: 4 up to 4 GPUs where the kernels still matter, "
                          "2 at 8, where few large NVLink copies win; profiles/r1_scaling.md)")
-    ap.add_argument("--gather", choices=["push", "nccl"], default="push")
+    ap.add_argument("--gather", choices=["f32-wire", "flags-only", "f64-full"], default="f32-wire",
+                    help="what the timed step gathers at N > 1 (the other two modes are timed beside it)")
     ap.add_argument("--push-streams", type=int, default=1)
     ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
     ap.add_argument("--no-cpu-baseline", action="store_true")

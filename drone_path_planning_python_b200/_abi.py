@@ -46,6 +46,7 @@ PROTOTYPES = {
     "mst_mesh_triangle_count": (ctypes.c_int, [c_void_p]),
     "mst_collide_poses": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
                                          c_void_p, c_void_p]),
+    "mst_collide_pose_sync": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "mst_collide_motions": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
                                            c_void_p, c_void_p]),
     "mst_collide_trajectories": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -57,6 +58,21 @@ PROTOTYPES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
 }
+
+
+class WireTargets(ctypes.Structure):
+    """``mst_wire_targets`` of include/mst.h: host arrays of device base pointers."""
+    _fields_ = [("count", ctypes.c_int),
+                ("pol_matrix", ctypes.POINTER(ctypes.c_void_p)),
+                ("hit", ctypes.POINTER(ctypes.c_void_p)),
+                ("any_hit", ctypes.POINTER(ctypes.c_void_p)),
+                ("row_offset", ctypes.c_longlong)]
+
+
+PROTOTYPES["mst_pipeline_wire"] = (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p, c_void_p, ctypes.POINTER(WireTargets), c_void_p,
+                                                  c_void_p])
 
 MST_OK = 0
 SOLVER_AUTO, SOLVER_BANDED_LU, SOLVER_CONDENSED = 0, 1, 2

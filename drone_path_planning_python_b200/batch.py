@@ -292,6 +292,21 @@ def collide_poses(robot: Mesh, env: Mesh, poses) -> torch.Tensor:
     return hit
 
 
+def collide_pose_now(robot: Mesh, env: Mesh, pose) -> int:
+    """One pose (3 | 4 | 7 doubles, host) -> 0 / 1, synchronously: the low-latency single query
+    behind ``Fcl_checker.check_collision`` (one launch + one stream synchronisation, no tensors)."""
+    _abi.require_cuda()
+    lib = _abi.load()
+    p = np.ascontiguousarray(pose, dtype=np.float64).reshape(-1)
+    if p.size not in (3, 4, 7):
+        raise ValueError("pose must have 3, 4 or 7 entries")
+    out = ctypes.c_int(-1)
+    rc = lib.mst_collide_pose_sync(robot.handle, env.handle, p.ctypes.data_as(ctypes.c_void_p), int(p.size),
+                                   ctypes.byref(out))
+    _abi.check(rc, "mst_collide_pose_sync")
+    return int(out.value)
+
+
 def collide_motions(robot: Mesh, env: Mesh, state_a, state_b, steps: int) -> torch.Tensor:
     """``state_a[M, 4]``, ``state_b[M, 4]`` (x, y, z, yaw) -> ``invalid[M]`` uint8: 1 iff one of the
     ``steps`` states interpolated at fractions ``j/steps`` (j = 1..steps) collides.  All
@@ -366,4 +381,67 @@ def pipeline(wp, t, S: int, robot: Mesh, env: Mesh, share_time_group: int = 1, s
                           _ptr(out.coef), _ptr(out.dur), _ptr(out.info), _ptr(out.hit), _ptr(out.any_hit),
                           _ptr(ws), _stream_ptr())
     _abi.check(rc, "mst_pipeline")
+    return out
+
+
+def make_wire_targets(pol_matrix=None, hit=None, any_hit=None, row_offset: int = 0):
+    """Build the ``mst_wire_targets`` block of ``pipeline_wire``: lists of CUDA tensors (this rank's
+    gather buffer and the peer mappings of the other ranks' buffers, e.g. from
+    ``torch.distributed._symmetric_memory``), one entry per destination.  Keeps the pointer arrays
+    alive on the returned object."""
+    lists = [x for x in (pol_matrix, hit, any_hit) if x is not None]
+    if not lists or len({len(x) for x in lists}) != 1:
+        raise ValueError("give pol_matrix and / or hit + any_hit, one tensor per destination each")
+    if (hit is None) != (any_hit is None):
+        raise ValueError("hit and any_hit travel together")
+    count = len(lists[0])
+    block = _abi.WireTargets()
+    block.count = count
+    block.row_offset = int(row_offset)
+    keep = []
+    for name, tensors in (("pol_matrix", pol_matrix), ("hit", hit), ("any_hit", any_hit)):
+        if tensors is None:
+            setattr(block, name, None)
+            continue
+        arr = (ctypes.c_void_p * count)(*[t.data_ptr() for t in tensors])
+        keep.append((arr, tensors))
+        setattr(block, name, ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p)))
+    block._keep = keep
+    return block
+
+
+def pipeline_wire(wp, t, S: int, robot: Mesh, env: Mesh, wire, share_time_group: int = 1,
+                  out: Optional[PipelineResult] = None) -> PipelineResult:
+    """``pipeline`` that ALSO stores the float32 polynomial matrix (the reference's wire format,
+    scripts/drones_pols_generator.py:63-77) and / or the flags through the destination pointers of
+    ``wire`` (``make_wire_targets``) from inside the kernel — the multi-GPU gather by NVLink peer
+    stores.  The caller closes the step with a cross-rank barrier."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    wp = _f64(wp, dev)
+    t = _f64(t, dev)
+    B, m, K = wp.shape
+    n = m - 1
+    G = int(share_time_group)
+    if n < 1:
+        raise IndexError("need at least two waypoints")
+    if G < 1 or B % G != 0 or t.shape[0] != B // G or t.shape[1] != m:
+        raise ValueError("t must be [B/share_time_group, n+1]")
+    if out is not None:
+        _check_out("out.coef", out.coef, (B, n, K, 8), torch.float64, dev)
+        _check_out("out.dur", out.dur, (B, n), torch.float64, dev)
+        _check_out("out.info", out.info, (B,), torch.int32, dev)
+        _check_out("out.hit", out.hit, (B, S), torch.uint8, dev)
+        _check_out("out.any_hit", out.any_hit, (B,), torch.uint8, dev)
+    else:
+        out = PipelineResult(torch.empty((B, n, K, 8), dtype=torch.float64, device=dev),
+                             torch.empty((B, n), dtype=torch.float64, device=dev),
+                             torch.empty((B,), dtype=torch.int32, device=dev),
+                             torch.empty((B, S), dtype=torch.uint8, device=dev),
+                             torch.empty((B,), dtype=torch.uint8, device=dev))
+    ws = torch.empty((max(1, lib.mst_pipeline_workspace_bytes(B, n, K, G, S)),), dtype=torch.uint8, device=dev)
+    rc = lib.mst_pipeline_wire(_ptr(wp), _ptr(t), B, n, K, G, S, robot.handle, env.handle, _ptr(out.coef), _ptr(out.dur),
+                               _ptr(out.info), _ptr(out.hit), _ptr(out.any_hit), ctypes.byref(wire), _ptr(ws),
+                               _stream_ptr())
+    _abi.check(rc, "mst_pipeline_wire")
     return out

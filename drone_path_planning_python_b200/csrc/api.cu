@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "mst_common.cuh"
+#include "onepass.cuh"
 
 namespace mst {
 
@@ -17,6 +18,18 @@ int check_launch() {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
   return MST_OK;
+}
+
+int sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
 }
 
 int allow_dynamic_smem(const void* kernel, size_t dynamic_bytes) {
@@ -60,7 +73,20 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 int launch_sample_collide(const double* coef, const double* dur, int B, int n, int K, int S,
                           const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const int* list = nullptr, const int* list_count = nullptr, int G = 1);
+int launch_onepass(const double* wp, const double* t, int groups, int n, int K, int G, int S, double* coef, double* dur,
+                   int* info, uint8_t* hit, uint8_t* any_hit, int* list, int* counters, const mst_mesh* robot,
+                   const mst_mesh* env, const WireTargets* wire, cudaStream_t stream);
+
+int launch_wire_patch(const double* coef, const double* dur, const uint8_t* hit, const uint8_t* any_hit, int n, int K,
+                      int G, int S, const int* list, const int* list_count, const WireTargets* wire,
+                      cudaStream_t stream);
+
+// MST_PIPELINE_TWO_PASS=1 forces the two-launch pipeline (solver kernel, then sample+collide kernel)
+static bool two_pass_forced() {
+  static const bool forced = getenv("MST_PIPELINE_TWO_PASS") != nullptr && atoi(getenv("MST_PIPELINE_TWO_PASS")) != 0;
+  return forced;
+}
 
 // Trajectories per pass of the pipeline (solver launch + fused sample/collide launch).
 // Measured on B200 (profiles/r1_chunk_sweep.txt): passes small enough to keep a pass's
@@ -234,12 +260,65 @@ extern "C" size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_ti
   return mst_solve_workspace_bytes(B, n, K, share_time_group);
 }
 
+// does the single-pass kernel take these sizes?  (mirrors launch_onepass's own checks, minus the meshes)
+static bool onepass_sizes(int n, int K, int G, int solver, int S) {
+  return !two_pass_forced() && solver == MST_SOLVER_AUTO && (K == 3 || K == 4) && G * K <= 32 && n >= 2 && n <= 32 &&
+         S >= 32 && S <= 4096 && banded_lu_smem_per_warp(n, G * K) <= MST_MAX_SMEM;
+}
+
 extern "C" int mst_pipeline_launch_count(int B, int n, int K, int share_time_group, int solver, int S) {
   if (B <= 0 || S < 1 || K < 1 || n < 1 || share_time_group < 1) return 0;
   const int chunk = pipeline_chunk(B, n, K, share_time_group);
   const int chunks = (B + chunk - 1) / chunk;
+  // single pass: the fused kernel + the two list-mode kernels behind it (pivoted solver, sampling of
+  // its groups; both exit at once when no group was handed over)
+  if (onepass_sizes(n, K, share_time_group, solver, S)) return chunks * 3;
   const int solve = solver == MST_SOLVER_AUTO ? 2 : 1;  // condensed (+ banded LU over the declined list)
   return chunks * (solve + 1);                           // + fused sample/collide/any-hit
+}
+
+static int pipeline_impl(const double* wp, const double* t, int B, int n, int K, int G, int solver, int S,
+                         mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,
+                         uint8_t* any_hit, const WireTargets* wire, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = pipeline_chunk(B, n, K, G);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    const double* wc = wp + (size_t)b0 * (n + 1) * K;
+    const double* tc = t + (size_t)(b0 / G) * (n + 1);
+    double* cc = coef + (size_t)b0 * n * K * MST_NCOEF;
+    double* dd = dur + (size_t)b0 * n;
+    uint8_t* hh = hit ? hit + (size_t)b0 * S : nullptr;
+    uint8_t* aa = any_hit ? any_hit + b0 : nullptr;
+    int rc = MST_ERR_TOO_LARGE;
+    if (onepass_sizes(n, K, G, solver, S)) {
+      int* counters = (int*)workspace;
+      int* list = counters + 64;
+      WireTargets wchunk;
+      if (wire) { wchunk = *wire; wchunk.row0 += b0; }
+      rc = launch_onepass(wc, tc, nb / G, n, K, G, S, cc, dd, info + b0, hh, aa, list, counters, robot, env,
+                          wire ? &wchunk : nullptr, st);
+      if (rc == MST_OK) {
+        // groups the condensed path must not take: pivoted solve, then their samples (list mode)
+        rc = launch_banded_lu(wc, tc, nb / G, n, K, G, list, counters, cc, dd, info + b0, st);
+        if (rc != MST_OK) return rc;
+        rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st, list, counters, G);
+        if (rc != MST_OK) return rc;
+        if (wire) {   // their wire rows, from the local results
+          rc = launch_wire_patch(cc, dd, hh, aa, n, K, G, S, list, counters, &wchunk, st);
+          if (rc != MST_OK) return rc;
+        }
+        continue;
+      }
+      if (rc != MST_ERR_TOO_LARGE) return rc;
+    }
+    if (wire) return MST_ERR_TOO_LARGE;   // the two-launch pipeline has no wire outputs
+    rc = mst_solve_batch(wc, tc, nb, n, K, G, solver, cc, dd, info + b0, workspace, stream);
+    if (rc != MST_OK) return rc;
+    rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st);
+    if (rc != MST_OK) return rc;
+  }
+  return MST_OK;
 }
 
 extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
@@ -249,19 +328,33 @@ extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int
   const int G = share_time_group;
   if (S < 1 || (K != 3 && K != 4) || !robot || !env || G < 1 || B < 0 || n < 1 || B % G != 0)
     return MST_ERR_INVALID;
+  if (solver != MST_SOLVER_AUTO && solver != MST_SOLVER_BANDED_LU && solver != MST_SOLVER_CONDENSED)
+    return MST_ERR_INVALID;
   if (B == 0) return MST_OK;
   if (!hit || !any_hit || !workspace || !wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int chunk = pipeline_chunk(B, n, K, G);
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
-    double* cc = coef + (size_t)b0 * n * K * MST_NCOEF;
-    double* dd = dur + (size_t)b0 * n;
-    int rc = mst_solve_batch(wp + (size_t)b0 * (n + 1) * K, t + (size_t)(b0 / G) * (n + 1), nb, n, K, G, solver,
-                             cc, dd, info + b0, workspace, stream);
-    if (rc != MST_OK) return rc;
-    rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hit + (size_t)b0 * S, any_hit + b0, st);
-    if (rc != MST_OK) return rc;
+  return pipeline_impl(wp, t, B, n, K, G, solver, S, robot, env, coef, dur, info, hit, any_hit, nullptr, workspace,
+                       stream);
+}
+
+extern "C" int mst_pipeline_wire(const double* wp, const double* t, int B, int n, int K, int share_time_group, int S,
+                                 mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur, int* info,
+                                 uint8_t* hit, uint8_t* any_hit, const mst_wire_targets* wire, void* workspace,
+                                 void* stream) {
+  const int G = share_time_group;
+  if (S < 1 || (K != 3 && K != 4) || !robot || !env || G < 1 || B < 0 || n < 1 || B % G != 0) return MST_ERR_INVALID;
+  if (!wire || wire->count < 1 || wire->count > MST_WIRE_MAX_TARGETS || wire->row_offset < 0) return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!workspace || !wp || !t || !coef || !dur || !info || !hit || !any_hit) return MST_ERR_INVALID;
+  WireTargets w;
+  memset(&w, 0, sizeof(w));
+  w.count = wire->count;
+  w.row0 = wire->row_offset;
+  for (int i = 0; i < wire->count; ++i) {
+    w.mat[i] = wire->pol_matrix ? wire->pol_matrix[i] : nullptr;
+    w.hit[i] = wire->hit ? wire->hit[i] : nullptr;
+    w.any[i] = wire->any_hit ? wire->any_hit[i] : nullptr;
+    if ((w.hit[i] == nullptr) != (w.any[i] == nullptr)) return MST_ERR_INVALID;
   }
-  return MST_OK;
+  return pipeline_impl(wp, t, B, n, K, G, MST_SOLVER_AUTO, S, robot, env, coef, dur, info, hit, any_hit, &w, workspace,
+                       stream);
 }

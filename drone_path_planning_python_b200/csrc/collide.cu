@@ -121,6 +121,37 @@ collide_motions_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBo
     ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single query with HOST arguments: the latency path of Fcl_checker.check_collision as OMPL's
+// isStateValid drives it, one state at a time (RB_planning_sep_coll_check.py:208-226).  One warp;
+// the pose is read from, and the answer written to, mapped pinned host memory, so a query is one
+// launch and one stream synchronisation — no staging copies, no allocation.  Meshes are read in
+// place from device memory (no shared-memory staging: nothing to amortise it over); the lanes
+// split the environment triangles and run the host-checkable culled routine, so meshes of any
+// size are accepted.
+__global__ void __launch_bounds__(32)
+collide_single_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
+                      const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
+                      const double* __restrict__ pose, int pose_dim, int* __restrict__ out) {
+  const MeshView rb = mesh_view(robot_img, rl);
+  const MeshView ev = mesh_view(env_img, el);
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, T[3];
+  if (pose_dim == 3) { T[0] = pose[0]; T[1] = pose[1]; T[2] = pose[2]; }
+  else pose_to_transform(pose, pose_dim, R, T);
+  const int lane = threadIdx.x;
+  bool h;
+  if (rb.V <= 64)   // vertex bit masks of the culled routine
+    h = pose_dim == 3 ? robot_hits_env_culled<false>(R, T, rb, rbb, ev, evb, true, lane, 32)
+                      : robot_hits_env_culled<true>(R, T, rb, rbb, ev, evb, pose_dim != 7, lane, 32);
+  else {
+    h = false;
+    for (int e = lane; e < ev.T && !h; e += 32)
+      h = robot_hits_env(R, T, rb.tri, rb.T, ev.tri + 9 * e, ev.box + 6 * e, 1, evb.root, rbb.radius, pose_dim != 7);
+  }
+  const unsigned any = __ballot_sync(0xffffffffu, h);
+  if (lane == 0) *out = any ? 1 : 0;
+}
+
 int launch_collide_motions(const mst_mesh* robot, const mst_mesh* env, const double* a, const double* b,
                            long long M, int steps, uint8_t* invalid, cudaStream_t stream) {
   if (M == 0) return MST_OK;
@@ -143,7 +174,9 @@ int launch_collide_motions(const mst_mesh* robot, const mst_mesh* env, const dou
 int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pose, long long P,
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;
-  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * collide_table_doubles(env->T, robot->V);
+  // the plane x vertex table serves translation-only poses alone
+  const size_t smem = robot->layout.bytes + env->layout.bytes +
+                      (pose_dim == 3 ? sizeof(double) * collide_table_doubles(env->T, robot->V) : 0);
   void (*kern)(const void*, MeshLayout, MeshBounds, const void*, MeshLayout, MeshBounds, const double*, long long,
                uint8_t*) = pose_dim == 3 ? collide_kernel<0> : (pose_dim == 4 ? collide_kernel<1> : collide_kernel<2>);
   {
@@ -194,4 +227,51 @@ extern "C" int mst_mesh_destroy(mst_mesh_t mesh) {
 }
 
 extern "C" int mst_mesh_triangle_count(mst_mesh_t mesh) { return mesh ? mesh->T : MST_ERR_INVALID; }
+
+namespace {
+// per calling thread: a stream and one page of mapped pinned memory (pose in, flag out)
+struct SyncSlot {
+  cudaStream_t stream = nullptr;
+  double* h_pose = nullptr;   // host view
+  double* d_pose = nullptr;   // device view of the same memory
+  int device = -1;
+};
+thread_local SyncSlot g_slot;
+
+int sync_slot(SyncSlot** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { mst::note_cuda_error(e); return MST_ERR_CUDA; }
+  if (g_slot.stream == nullptr || g_slot.device != dev) {
+    if (g_slot.h_pose) cudaFreeHost(g_slot.h_pose);
+    if (g_slot.stream) cudaStreamDestroy(g_slot.stream);
+    g_slot = SyncSlot();
+    e = cudaStreamCreateWithFlags(&g_slot.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&g_slot.h_pose, 256, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&g_slot.d_pose, g_slot.h_pose, 0);
+    if (e != cudaSuccess) { mst::note_cuda_error(e); g_slot = SyncSlot(); return MST_ERR_CUDA; }
+    g_slot.device = dev;
+  }
+  *out = &g_slot;
+  return MST_OK;
+}
+}  // namespace
+
+extern "C" int mst_collide_pose_sync(mst_mesh_t robot, mst_mesh_t env, const double* pose, int pose_dim, int* hit) {
+  if (!robot || !env || !pose || !hit || (pose_dim != 3 && pose_dim != 4 && pose_dim != 7)) return MST_ERR_INVALID;
+  SyncSlot* slot = nullptr;
+  const int rc = sync_slot(&slot);
+  if (rc != MST_OK) return rc;
+  for (int i = 0; i < pose_dim; ++i) slot->h_pose[i] = pose[i];
+  int* h_out = reinterpret_cast<int*>(slot->h_pose + 8);
+  int* d_out = reinterpret_cast<int*>(slot->d_pose + 8);
+  *h_out = -1;
+  mst::collide_single_kernel<<<1, 32, 0, slot->stream>>>(robot->d_image, robot->layout, robot->bounds, env->d_image,
+                                                        env->layout, env->bounds, slot->d_pose, pose_dim, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(slot->stream);
+  if (e != cudaSuccess) { mst::note_cuda_error(e); return MST_ERR_CUDA; }
+  *hit = *h_out;
+  return MST_OK;
+}
 

@@ -195,10 +195,13 @@ __host__ __device__ __forceinline__ float round_up_f(double x) {
 // This is the host-checkable statement of the culls the warp engine below applies (the engine
 // keeps them as sets of robot triangles and uses the interval pair test).
 // ROT = false: translation only (R = identity), the K = 3 pipeline.
+// e_first / e_step: the environment triangles e_first, e_first + e_step, ... only (the single-query
+// kernel spreads them over the lanes of a warp); 0 / 1 = all of them.
 template <bool ROT>
 __host__ __device__ inline bool robot_hits_env_culled(const double* R, const double* T, const MeshView& rb,
                                                       const MeshBounds& rbb, const MeshView& ev,
-                                                      const MeshBounds& evb, bool rigid) {
+                                                      const MeshBounds& evb, bool rigid, int e_first = 0,
+                                                      int e_step = 1) {
   const double* root = evb.root;
   if (rigid && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
                 T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
@@ -226,7 +229,7 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
     return false;
   const float flo0 = round_down_f(lo0), flo1 = round_down_f(lo1), flo2 = round_down_f(lo2);
   const float fhi0 = round_up_f(hi0), fhi1 = round_up_f(hi1), fhi2 = round_up_f(hi2);
-  for (int e = 0; e < ev.T; ++e) {
+  for (int e = e_first; e < ev.T; e += e_step) {
     const double* bx = ev.box + 6 * e;
     const float* fb = ev.fbox + 8 * e;
     if (fhi0 < fb[0] || flo0 > fb[3] || fhi1 < fb[1] || flo1 > fb[4] || fhi2 < fb[2] || flo2 > fb[5]) continue;

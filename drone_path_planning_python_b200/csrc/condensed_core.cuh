@@ -240,6 +240,40 @@ __host__ __device__ inline void condensed_backward(const double* __restrict__ wp
   }
 }
 
+// phase 3 without the coefficients: back sweep knot n-1 .. 1 that leaves the knot state
+// (velocity, acceleration, jerk) of column k at knot i IN PLACE of y_i, i.e. at
+// ys[((i-1)*3*K + 3*k + j) * ystride].  Same arithmetic as the first half of condensed_backward;
+// the single-pass pipeline (pipeline_onepass.cu) keeps these 3 values per knot and column on chip
+// — a third of the 8 coefficients per piece — and forms the coefficients of a trajectory with
+// piece_coefficients() right before its samples are evaluated and its rows are stored.
+template <int KC>
+__host__ __device__ inline void condensed_backward_states(int n, int K, const double* rho, const double* fac,
+                                                          int fstride, double* ys, int ystride) {
+  const int stride = fstride;
+  double xv[KC], xa[KC], xj[KC];  // state at knot i+1
+#pragma unroll
+  for (int k = 0; k < KC; ++k) xv[k] = xa[k] = xj[k] = 0.0;
+  for (int i = n - 1; i >= 1; --i) {
+    const double rh = rho[(size_t)i * stride];
+    const RhoPow pb = rho_powers(rh);
+    const Mat3 b = coupling_block(pb);  // B_i
+    const Ldl3 f = load_factor(fac, i, stride);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      if (k < K) {
+        double* yo = ys + ((size_t)(i - 1) * 3 * K + 3 * k) * ystride;
+        const double b1 = yo[0] - (b.m11 * xv[k] + b.m12 * xa[k] + b.m13 * xj[k]);
+        const double b2 = yo[ystride] - (b.m21 * xv[k] + b.m22 * xa[k] + b.m23 * xj[k]);
+        const double b3 = yo[2 * (size_t)ystride] - (b.m31 * xv[k] + b.m32 * xa[k] + b.m33 * xj[k]);
+        double nv, na, nj;
+        ldl3_solve(f, b1, b2, b3, nv, na, nj);
+        yo[0] = nv; yo[ystride] = na; yo[2 * (size_t)ystride] = nj;
+        xv[k] = nv; xa[k] = na; xj[k] = nj;
+      }
+    }
+  }
+}
+
 // classification of a time group; returns 0 = condensed path may run,
 // 1 = decline (needs the pivoted solver), 2 = decreasing times, 3 = non-finite times
 __host__ __device__ inline int classify_times(const double* tg, int n, double* Tmin_out, double* Tmax_out) {

@@ -6,7 +6,7 @@
 #include "../../include/mst.h"
 
 #define MST_NCOEF 8
-#define MST_SM_COUNT 148            // B200: 2 dies x 74 SMs
+#define MST_SM_COUNT (mst::sm_count())  // SMs of the current device (148 on B200: 2 dies x 74)
 #define MST_MAX_SMEM (227 * 1024)   // opt-in dynamic shared memory per CTA
 
 namespace mst {
@@ -17,6 +17,8 @@ int check_launch();
 // opt a kernel in to `dynamic_bytes` of dynamic shared memory (on top of its static usage);
 // MST_ERR_TOO_LARGE when static + dynamic exceed what one CTA can have on sm_100a
 int allow_dynamic_smem(const void* kernel, size_t dynamic_bytes);
+// multiprocessor count of the current device (queried once per device)
+int sm_count();
 
 // k!/(k-j)! for 0 <= j <= k <= 7 (exact in double)
 __host__ __device__ __forceinline__ double falling_factorial(int k, int j) {

@@ -41,12 +41,23 @@ constexpr int FUSED_WT_MAX = 32; // trajectories per warp tile (chosen by the la
 // appended (ballot-compacted) to the warp's pose ring, and only when 32 of them are waiting
 // does the warp run the collision engine (collide_core.cuh) — on a DENSE batch, whatever mix
 // of near and far samples the trajectories produce.
-template <int K, bool TAB>
+// LIST = true: only the trajectories of the time groups in list[0 .. *list_count) are worked on
+// (trajectory j of the launch is list[j / G] * G + j % G) — the groups the single-pass pipeline
+// handed to the pivoted solver; the kernel exits at once when the list is empty.
+template <int K, bool TAB, bool LIST>
 __global__ void __launch_bounds__(FUSED_THREADS, 4)
 sample_collide_kernel(const double* __restrict__ coef, const double* __restrict__ dur, int B, int n, int S, int FUSED_WT,
                       const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
                       const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
-                      uint8_t* __restrict__ hit, uint8_t* __restrict__ any_hit) {
+                      uint8_t* __restrict__ hit, uint8_t* __restrict__ any_hit, const int* __restrict__ list,
+                      const int* __restrict__ list_count, int G) {
+  if (LIST) {
+    const int listed = *list_count;
+    if (listed == 0) return;
+    B = listed * G;
+  }
+  // launch-local trajectory index -> trajectory of the batch
+  auto bmap = [&](int j) -> size_t { return LIST ? (size_t)list[j / G] * G + (size_t)(j % G) : (size_t)j; };
   constexpr int POSE = K == 3 ? 0 : 1;
   constexpr int NP = PoseDim<POSE>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -63,7 +74,7 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
   if (engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
   __syncthreads();
-  double* tables = nv + (engine ? collide_table_doubles(ev.T, rb.V) : 0);
+  double* tables = nv + ((engine && POSE == 0) ? collide_table_doubles(ev.T, rb.V) : 0);
   double* knots = tables + warp * FUSED_WT * (n + 2);
   double* dts = knots + FUSED_WT * (n + 1);
   // thr[WT][n]: first sample index of pieces 1 .. n-1, and (when the launcher found room: TAB)
@@ -94,17 +105,19 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     const int next_b0 = next_tile < tiles ? (int)(next_tile * FUSED_WT) : B;
     const int next_nb = min(FUSED_WT, B - next_b0);
     {
-      const char* dbase = reinterpret_cast<const char*>(dur + (size_t)next_b0 * n);
-      const size_t dbytes = (size_t)max(next_nb, 0) * n * sizeof(double);
+      if (!LIST) {
+        const char* dbase = reinterpret_cast<const char*>(dur + (size_t)next_b0 * n);
+        const size_t dbytes = (size_t)max(next_nb, 0) * n * sizeof(double);
 #pragma unroll 1
-      for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
+        for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
+      }
     }
     // q-th trajectory of this warp counted from the start of the tile; runs on into the next tile
     auto prefetch_trajectory = [&](int q) {
       const int b = q < nb ? b0 + q : (q - nb < next_nb ? next_b0 + (q - nb) : -1);
       if (b >= 0) {
-        const char* cbase = reinterpret_cast<const char*>(coef) + (size_t)b * traj_bytes;
+        const char* cbase = reinterpret_cast<const char*>(coef) + bmap(b) * traj_bytes;
 #pragma unroll 1
         for (int off = lane * 128; off < traj_bytes; off += 32 * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + off));
@@ -112,14 +125,14 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     };
     __syncwarp();  // previous tile's tables are no longer read
     if (lane < nb) {
-      const double* T = dur + (size_t)(b0 + lane) * n;
+      const double* T = dur + bmap(b0 + lane) * n;
       double* kn = knots + lane * (n + 1);
       double acc = 0.0;
       kn[0] = 0.0;
 #pragma unroll 1
       for (int i = 0; i < n; ++i) { acc = __dadd_rn(acc, T[i]); kn[i + 1] = acc; }
       dts[lane] = __ddiv_rn(acc, (double)S);
-      any_hit[b0 + lane] = 0;
+      any_hit[bmap(b0 + lane)] = 0;
     }
     __syncwarp();
     // thresholds: first s with !(s * dt < knot), found from the quotient and corrected with the
@@ -179,7 +192,8 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
         }
       }
       const double local = __dsub_rn(t, kn[piece]);
-      const double* cp = coef + (((size_t)(b0 + tl) * n + piece) * K) * MST_NCOEF;
+      const size_t btl = bmap(b0 + tl);
+      const double* cp = coef + ((btl * n + piece) * K) * MST_NCOEF;
       double pos[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
@@ -201,12 +215,12 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       if (!engine) {  // meshes the bit-mask cursors cannot hold: plain per-lane test over all pairs
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         if (POSE == 1) quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
-        if (active) report(b0 + tl, s, robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true));
+        if (active) report((int)btl, s, robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true));
         continue;
       }
       const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
-      if (active && !near) hit[(size_t)b0 * S + idx] = 0;
-      ring_push<POSE>(ring, ring_tail, near, pp, b0 + tl, s, -1, 0u, 0u);
+      if (active && !near) hit[btl * S + s] = 0;
+      ring_push<POSE>(ring, ring_tail, near, pp, (int)btl, s, -1, 0u, 0u);
       while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
     }
   }
@@ -214,9 +228,11 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
+// list / list_count (device) non-null: list mode over the time groups of G trajectories named there;
+// B is then the size of the whole batch (upper bound of the work)
 int launch_sample_collide(const double* coef, const double* dur, int B, int n, int K, int S,
                           const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const int* list, const int* list_count, int G) {
   if (B == 0) return MST_OK;
   // trajectories per warp tile: large tiles amortise the per-tile set-up and leave fewer
   // half-empty last iterations (3.94 ms at 16 vs 4.13 ms at 4 per 1 M trajectories); bounded by
@@ -229,10 +245,18 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
   const bool tab = n <= 255 && S <= 1024;
   const size_t per_traj = sizeof(double) * (size_t)(n + 2) + sizeof(int) * (size_t)n + (tab ? (size_t)S : 0);
   while (FUSED_WT > 1 && FUSED_WARPS * FUSED_WT * per_traj > 24 * 1024) FUSED_WT /= 2;
-  const size_t smem = robot->layout.bytes + env->layout.bytes + sizeof(double) * collide_table_doubles(env->T, robot->V) +
+  // the plane x vertex table serves translation-only poses (K = 3) alone
+  const size_t smem = robot->layout.bytes + env->layout.bytes +
+                      (K == 3 ? sizeof(double) * collide_table_doubles(env->T, robot->V) : 0) +
                       FUSED_WARPS * FUSED_WT * per_traj;
-  auto kern = K == 3 ? (tab ? sample_collide_kernel<3, true> : sample_collide_kernel<3, false>)
-                     : (tab ? sample_collide_kernel<4, true> : sample_collide_kernel<4, false>);
+  void (*kern)(const double*, const double*, int, int, int, int, const void*, MeshLayout, MeshBounds, const void*,
+               MeshLayout, MeshBounds, uint8_t*, uint8_t*, const int*, const int*, int);
+  if (list)
+    kern = K == 3 ? (tab ? sample_collide_kernel<3, true, true> : sample_collide_kernel<3, false, true>)
+                  : (tab ? sample_collide_kernel<4, true, true> : sample_collide_kernel<4, false, true>);
+  else
+    kern = K == 3 ? (tab ? sample_collide_kernel<3, true, false> : sample_collide_kernel<3, false, false>)
+                  : (tab ? sample_collide_kernel<4, true, false> : sample_collide_kernel<4, false, false>);
   {
     const int rc = allow_dynamic_smem((const void*)kern, smem);
     if (rc != MST_OK) return rc;
@@ -243,7 +267,7 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
   if (blocks > cap) blocks = cap;
   kern<<<blocks, FUSED_THREADS, smem, stream>>>(coef, dur, B, n, S, FUSED_WT, robot->d_image, robot->layout,
                                                  robot->bounds, env->d_image, env->layout, env->bounds, hit,
-                                                 any_hit);
+                                                 any_hit, list, list_count, G);
   return check_launch();
 }
 

@@ -58,7 +58,7 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
     for (int i = lane; i < n; i += 32) {
       const double T = tg[i + 1] - tg[i];
       Ts[i] = T;
-      if (!(T >= 0.0)) bad = max(bad, isfinite(T) ? 1 : 2);
+      if (!(T >= 0.0) || !isfinite(T)) bad = max(bad, isfinite(T) ? 1 : 2);   // +inf counts as non-finite input
     }
     bad = __reduce_max_sync(FULL, bad);
     for (int e = lane; e < G * n; e += 32)

@@ -137,3 +137,55 @@ class PeerPushAllGather:
             cur.wait_stream(side)
         self.handles[0].barrier(channel=1)          # every peer's pushes into this buffer have landed
         return self.out
+
+
+class PeerStoreGather:
+    """All-gather by PEER STORES from inside the pipeline kernel (``mst_pipeline_wire``).
+
+    Every rank owns symmetric buffers ``[world * count, ...]`` for the wire outputs — the float32
+    polynomial matrix the reference's ``path_to_pol`` emits (scripts/drones_pols_generator.py:63-77)
+    and / or the collision flags — mapped by all peers over NVLink
+    (``torch.distributed._symmetric_memory``).  The single-pass kernel stores each finished
+    trajectory's rows through all ``world`` base pointers (its own buffer first, then the peers,
+    staggered by rank so the links load evenly): the exchange is spread over the whole kernel, no
+    copy engine or collective kernel runs, and a device-side barrier on the signal pads closes the
+    step.  ``mode``: ``"pol_matrix_f32"`` (matrix + flags) or ``"flags"`` (flags only).
+    After ``run`` the local buffers hold all ranks' results in GLOBAL trajectory order.
+    """
+
+    def __init__(self, count: int, world: int, rank: int, n: int, K: int, S: int, device, mode: str = "pol_matrix_f32"):
+        import torch.distributed._symmetric_memory as symm
+        from .batch import make_wire_targets
+        if mode not in ("pol_matrix_f32", "flags"):
+            raise ValueError("mode must be 'pol_matrix_f32' or 'flags'")
+        if world > 8:
+            raise ValueError("at most 8 destinations (one NVSwitch domain)")
+        self.count, self.world, self.rank, self.mode = count, world, rank, mode
+        gname = dist.group.WORLD.group_name
+        rows = world * count
+        specs = []
+        if mode == "pol_matrix_f32":
+            specs.append(("pol_matrix", (rows, n, 1 + 8 * K), torch.float32))
+        specs += [("hit", (rows, S), torch.uint8), ("any_hit", (rows,), torch.uint8)]
+        self.buffers, self.handles, order = {}, [], [(rank + shift) % world for shift in range(world)]
+        targets = {}
+        for name, shape, dtype in specs:
+            buf = symm.empty(shape, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, gname)
+            self.buffers[name] = buf
+            self.handles.append(hdl)
+            targets[name] = [buf if p == rank else hdl.get_buffer(p, shape, dtype) for p in order]
+        self.wire = make_wire_targets(targets.get("pol_matrix"), targets["hit"], targets["any_hit"],
+                                      row_offset=rank * count)
+        self._targets = targets
+
+    def bytes_per_trajectory(self, n: int, K: int, S: int) -> int:
+        return (n * (1 + 8 * K) * 4 if self.mode == "pol_matrix_f32" else 0) + S + 1
+
+    def run(self, launch: Callable[[object], None]):
+        """``launch(wire)`` must issue ``pipeline_wire(..., wire)`` for this rank's trajectories on
+        the current stream."""
+        self.handles[0].barrier(channel=0)          # peers are done reading the previous step
+        launch(self.wire)
+        self.handles[0].barrier(channel=1)          # every peer's stores into this buffer have landed
+        return self.buffers

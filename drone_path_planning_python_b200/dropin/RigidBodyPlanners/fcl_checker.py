@@ -91,9 +91,9 @@ class Fcl_checker():
     def check_collision(self, T=None, q=[0, 0, 0, 1]):
         if T is not None:
             self.robot.set_transform(T, q)
-        hit = _mst.collide_poses(self.robot.m, self.env.m, self.robot.pose()[None, :])
-        # fcl.collide returns the number of contacts: 0 or 1 for the default request
-        return int(hit[0])
+        # one launch + one stream synchronisation (mst_collide_pose_sync); fcl.collide returns the
+        # number of contacts: 0 or 1 for the default request
+        return _mst.collide_pose_now(self.robot.m, self.env.m, self.robot.pose())
 
     def set_robot_transform(self, T, q=[0, 0, 0, 1]):
         self.robot.set_transform(T, q)

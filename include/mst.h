@@ -211,6 +211,17 @@ int mst_collide_poses(mst_mesh_t robot, mst_mesh_t env, const double* pose, int 
                       int pose_dim, uint8_t* hit, void* stream);
 
 /*
+ * One collision query with HOST arguments, synchronous — the latency path of
+ * Fcl_checker.check_collision when OMPL calls isStateValid one state at a time
+ * (src/RigidBodyPlanners/RB_planning_sep_coll_check.py:208-226).  `pose` (pose_dim doubles, as in
+ * mst_collide_poses) and `hit` are HOST pointers; the call returns after the answer (0 / 1) is in
+ * *hit.  One launch + one stream synchronisation on a per-thread stream, pose and answer travel
+ * through mapped pinned memory (allocated on a thread's first call: the one exception to "no
+ * allocation after mst_mesh_create"); safe to call from several threads.  Meshes of any size.
+ */
+int mst_collide_pose_sync(mst_mesh_t robot, mst_mesh_t env, const double* pose, int pose_dim, int* hit);
+
+/*
  * Batched motion validation for the sampling planner: M candidate motions
  * between states (x, y, z, yaw); each is checked at `steps` states interpolated linearly at
  * fractions j/steps, j = 1..steps (end state included, start state assumed valid) — what OMPL's
@@ -234,6 +245,9 @@ int mst_collide_trajectories(const double* coef, const double* dur, int B, int n
 /*
  * Fused pipeline: solve -> sample S uniform times -> place the robot mesh at every
  * sampled position (yaw = sampled 4th axis when K = 4, else 0) -> collide.
+ * One persistent kernel (the coefficients reach HBM once and are never read back) when the sizes
+ * suit it (K = 3 / 4, 2 <= n <= 32, 32 <= S <= 4096, G*K <= 32, MST_SOLVER_AUTO); the two-launch
+ * pipeline (solver, then sample + collide) otherwise.  Results are identical either way.
  *   inputs / coef / dur / info as mst_solve_batch
  *   hit     [B][S]  per-sample collision flag
  *   any_hit [B]     1 iff any sample of the trajectory collides
@@ -246,6 +260,32 @@ int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
                  int share_time_group, int solver, int S, mst_mesh_t robot,
                  mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,
                  uint8_t* any_hit, void* workspace, void* stream);
+
+/*
+ * Fused pipeline with WIRE outputs for the multi-GPU gather ("all-gather ... only for
+ * the final coefficients and collision flags").  Besides the local results of mst_pipeline, the
+ * kernel stores, tile by tile while it computes, what the reference's path_to_pol emits — the
+ * float32 polynomial matrix [T | x0..x7 | y0..y7 | z0..z7 (| yaw0..yaw7)] per piece
+ * (scripts/drones_pols_generator.py:63-77) — and / or the collision flags through `count` base
+ * pointers: this rank's own gather buffer and the NVLink peer mappings of the other ranks'
+ * buffers (e.g. torch.distributed._symmetric_memory).  Rows [row_offset, row_offset + B) of every
+ * buffer are this rank's.  The stores to peer pointers ARE the all-gather; the caller closes the
+ * step with a cross-rank barrier.  Solver selection is MST_SOLVER_AUTO.
+ *   pol_matrix[i] -> [rows][n][1 + 8K] float32, hit[i] -> [rows][S], any_hit[i] -> [rows]
+ *   (pol_matrix == NULL or hit == NULL / any_hit == NULL: that output is not gathered)
+ * The three pointer arrays live in HOST memory; the pointers in them are device pointers.
+ */
+#define MST_WIRE_MAX_TARGETS 8
+typedef struct mst_wire_targets {
+  int count;
+  float* const* pol_matrix;
+  uint8_t* const* hit;
+  uint8_t* const* any_hit;
+  long long row_offset;
+} mst_wire_targets;
+int mst_pipeline_wire(const double* wp, const double* t, int B, int n, int K, int share_time_group, int S,
+                      mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,
+                      uint8_t* any_hit, const mst_wire_targets* wire, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,52 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+REF_SRC = "/root/reference/src/optimizations"
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+def populate_ref() -> bool:
+    """Place the UNMODIFIED reference trajectory package under the git-ignored ``oracle/_ref/`` (it
+    then travels to the GPU box with the snapshot, where /root/reference does not exist).  The
+    reference is pure Python: there is nothing to compile.  Only ``bench.py``'s CPU arm imports it
+    (``import_ref``).  Returns whether ``oracle/_ref/optimizations`` is available."""
+    import shutil
+    dst = os.path.join(REF_DIR, "optimizations")
+    if os.path.isdir(REF_SRC):
+        os.makedirs(REF_DIR, exist_ok=True)
+        if os.path.isdir(dst):
+            shutil.rmtree(dst)
+        shutil.copytree(REF_SRC, dst, ignore=shutil.ignore_patterns("__pycache__"))
+    return os.path.isfile(os.path.join(dst, "calculatingTrajectories.py"))
+
+
+def import_ref():
+    """Import the unmodified reference package from ``oracle/_ref`` (None when absent).  matplotlib /
+    mpl_toolkits are not in the image and only used by its plotting helper, so empty stand-in
+    modules are registered first (as oracle/make_golden.py does); no reference file is touched."""
+    import importlib.util
+    import sys
+    import types
+    import warnings
+    init = os.path.join(REF_DIR, "optimizations", "__init__.py")
+    if not os.path.isfile(init):
+        return None
+    warnings.filterwarnings("ignore")
+    for name in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if not hasattr(sys.modules["mpl_toolkits.mplot3d"], "Axes3D"):
+        sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    spec = importlib.util.spec_from_file_location("_reference_optimizations", init,
+                                                  submodule_search_locations=[os.path.dirname(init)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_reference_optimizations"] = mod
+    spec.loader.exec_module(mod)
+    import importlib
+    ct = importlib.import_module("_reference_optimizations.calculatingTrajectories")
+    return mod, ct
+
+
 _lib = None
 
 

@@ -213,8 +213,89 @@ def test_pipeline_answers_every_sample():
         assert torch.equal(res.any_hit, res.hit.amax(dim=1))
 
 
+def test_mesh_level_exact_anchors(golden_dir):
+    """Kernels vs the robot-pose-vs-environment answers decided in exact rational arithmetic on the
+    shipped mesh pairs (tests/golden/collision_anchors.npz, oracle/make_collision_anchors.py; the
+    predicate fcl.collide decides at fcl_checker.py:93-100): lattice poses, exact half turns, shared
+    corners (touching = collision) and the pose the reference itself evaluates (fcl_checker.py:133-136).
+    Every answer must match — no epsilon band."""
+    import os
+    import sys
+    import drone_path_planning_python_b200 as mst
+    with np.load(os.path.join(golden_dir, "collision_anchors.npz")) as z:
+        data = {k: z[k] for k in z.files}
+    seen_reference_pose = False
+    for i in range(4):
+        key = "pair%d__" % i
+        robot, env = mst.Mesh(_soup(str(data[key + "robot"]))), mst.Mesh(_soup(str(data[key + "env"])))
+        poses, exact, kind = data[key + "poses"], data[key + "exact"], data[key + "kind"]
+        hit = mst.collide_poses(robot, env, poses).cpu().numpy()
+        assert np.array_equal(hit, exact), (str(data[key + "env"]), np.flatnonzero(hit != exact))
+        # pure translations among them through the translation-only kernel as well
+        ident = (poses[:, 3:] == [0, 0, 0, 1]).all(axis=1)
+        hit3 = mst.collide_poses(robot, env, poses[ident, :3]).cpu().numpy()
+        assert np.array_equal(hit3, exact[ident])
+        if (kind == 2).any():
+            seen_reference_pose = True
+            j = int(np.flatnonzero(kind == 2)[0])
+            assert exact[j] == 0 and hit[j] == 0
+            # the same query through the drop-in, the way fcl_checker.py:124-136 issues it
+            sys.path.insert(0, mst.dropin_path())
+            try:
+                from RigidBodyPlanners.fcl_checker import Fcl_checker
+                import tempfile
+                from drone_path_planning_python_b200 import meshio
+                with tempfile.TemporaryDirectory() as tmp:
+                    ef, rf = os.path.join(tmp, "env.stl"), os.path.join(tmp, "robot.stl")
+                    meshio.write_stl(ef, meshio.shipped_mesh("env-scene-ltu-experiment"))
+                    meshio.write_stl(rf, meshio.shipped_mesh("robot-scene-triangle"))
+                    checker = Fcl_checker(ef, rf)
+                    checker.set_robot_transform([-1.21917, -0.441611, -0.0462389],
+                                                [-0.298798, 0.00548747, 0.0160421, 0.954166])
+                    assert checker.check_collision() == 0
+            finally:
+                sys.path.remove(mst.dropin_path())
+                for name in [m for m in sys.modules if m.split(".")[0] == "RigidBodyPlanners"]:
+                    del sys.modules[name]
+    assert seen_reference_pose
+
+
+def test_state_validity_loop_equals_batch(tmp_path):
+    """2,000 isStateValid-style single queries through the Fcl_checker drop-in
+    (RB_planning_sep_coll_check.py:208-215: set pose, check_collision, `not collision`) give the
+    same answers as one check_collision_batch launch and as the oracle outside the touching band."""
+    import sys
+    import drone_path_planning_python_b200 as mst
+    from drone_path_planning_python_b200 import meshio
+    from oracle import collision_oracle as co
+    sys.path.insert(0, mst.dropin_path())
+    try:
+        from RigidBodyPlanners.fcl_checker import Fcl_checker
+        ef, rf = str(tmp_path / "env.stl"), str(tmp_path / "robot.stl")
+        meshio.write_stl(ef, meshio.shipped_mesh("env-scene-ltu-experiment"))
+        meshio.write_stl(rf, meshio.shipped_mesh("custom_triangle_robot"))
+        checker = Fcl_checker(ef, rf)
+        rng = np.random.default_rng(99)
+        states = _random_poses(rng, 2000, 4)
+        single = np.zeros(2000, np.uint8)
+        for i, st in enumerate(states):
+            q = co.yaw_pose_quat(st[3])
+            single[i] = checker.check_collision(st[:3], q)
+        batch = checker.check_collision_batch(states)
+        assert np.array_equal(single, batch)
+        ref, margin = co.collide_poses(_soup("custom_triangle_robot"), _soup("env-scene-ltu-experiment"), states,
+                                       with_margin=True)
+        clear = np.abs(margin) > EPS
+        assert np.array_equal(single[clear], ref[clear]) and 0.02 < single.mean() < 0.9
+    finally:
+        sys.path.remove(mst.dropin_path())
+        for name in [m for m in sys.modules if m.split(".")[0] == "RigidBodyPlanners"]:
+            del sys.modules[name]
+
+
 def test_batched_motion_validation():
-    """mst_collide_motions == checking every interpolated state separately."""
+    """mst_collide_motions == checking every interpolated state separately, and == the oracle on
+    the interpolated states (C restatement) outside the touching band."""
     import drone_path_planning_python_b200 as mst
     rng = np.random.default_rng(17)
     robot_tris, env_tris = _soup("custom_triangle_robot"), _soup("env-scene-ltu-experiment")
@@ -228,6 +309,16 @@ def test_batched_motion_validation():
     each = mst.collide_poses(robot, env, states.reshape(-1, 4)).cpu().numpy().reshape(M, steps)
     assert np.array_equal(invalid, each.max(axis=1))
     assert 0.05 < invalid.mean() < 0.95
+    # against the oracle (not another kernel): the C restatement on the same interpolated states of a
+    # subset of the motions; a motion may differ only if one of its states sits in the touching band
+    from oracle import build_oracle, collision_oracle as co
+    sub = slice(0, 600)
+    ref_each = build_oracle.c_collide_poses(robot_tris, env_tris, states[sub].reshape(-1, 4)).reshape(-1, steps)
+    ref_invalid = ref_each.max(axis=1)
+    for m in np.flatnonzero(ref_invalid != invalid[sub]):
+        _, margin = co.collide_poses(robot_tris, env_tris, states[m], with_margin=True)
+        assert np.abs(margin).min() <= 1e-7, m
+    assert (ref_invalid != invalid[sub]).mean() < 0.01
     # the planner's own straight line start -> goal crosses the wall (scripts/rigidBodyPath.py:146-147)
     assert mst.collide_motions(robot, env, [[0, 3, 1, 0]], [[0, 5, 1, 0]], 2000).cpu().numpy().tolist() == [1]
     assert mst.collide_motions(robot, env, [[0, 3, 1, 0]], [[1, 3.2, 1.2, 0.5]], 2000).cpu().numpy().tolist() == [0]

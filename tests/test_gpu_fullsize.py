@@ -53,6 +53,62 @@ def _check_system(coef, dur, wp, rtol=2e-9):
         assert (end[:, -1, :, j].abs() * T[:, -1] ** j <= 50 * rtol * scale[:, 0, :, 0]).all()
 
 
+def test_config1_shipped_example_with_third_drone(golden_dir):
+    """BASELINE configs[0]: the shipped 3-drone formation example.  Rigid-body
+    path recovered from Pol_matrix_{1,2}.csv (50 waypoints, T = 0.2, n = 49, K = 4); drones 1, 2 at
+    (+-0.5, 0, 0) and the synthetic third drone at rb + R_z(yaw) (0, 0, -0.5) that the robot mesh
+    implies; formation transform, min-snap solve with the formation sharing one time vector, float32
+    packing and sampling on the GPU — against the oracle (restatement pinned bit for bit to the
+    reference) in coefficient and position space, and against the shipped CSVs in position space."""
+    import os
+    from oracle import collision_oracle as co, minsnap_oracle as mo
+    import drone_path_planning_python_b200 as mst
+    with np.load(os.path.join(golden_dir, "shipped_pol_matrices.npz")) as z:
+        m1, m2 = z["Pol_matrix_1"].astype(np.float64), z["Pol_matrix_2"].astype(np.float64)
+
+    def waypoints(mat):
+        c = mat[:, 1:].reshape(-1, 4, 8)
+        w = np.zeros((50, 4))
+        w[:49] = c[:, :, 0]
+        w[49] = [mo.horner(c[48, k], mat[48, 0]) for k in range(4)]
+        return w
+    w1, w2 = waypoints(m1), waypoints(m2)
+    rb = np.concatenate([0.5 * (w1[:, :3] + w2[:, :3]), w1[:, 3:4]], axis=1)[None]       # [1, 50, 4]
+    offsets = np.array([[0.5, 0, 0], [-0.5, 0, 0], [0, 0, -0.5]])
+    t = mo.uniform_times(50)                                                              # drones_pols_generator.py:44-56
+    wp = mst.formation_waypoints(rb, offsets, K=4)
+    ref_wp = mo.formation_waypoints(rb[0], offsets)
+    assert np.abs(wp.cpu().numpy() - ref_wp).max() <= 1e-14
+    assert np.abs(wp[0].cpu().numpy()[:, :3] - w1[:, :3]).max() < 2e-6 and np.abs(wp[1].cpu().numpy()[:, :3] - w2[:, :3]).max() < 2e-6
+    # the third drone hangs 0.5 m below the rigid body whatever the yaw
+    assert np.abs(wp[2].cpu().numpy()[:, :3] - (rb[0, :, :3] + [0, 0, -0.5])).max() <= 1e-14
+    for solver in ("auto", "banded_lu"):
+        coef, dur, info = mst.solve_batch(wp, t[None], share_time_group=3, solver=solver)
+        assert int((info != 0).sum()) == 0
+        ts = np.arange(0, 9.8, 0.1)
+        pos = mst.sample_batch(coef, dur, ts=ts).cpu().numpy()
+        for d in range(3):
+            ref, rdur = mo.solve_waypoints(ref_wp[d], t)
+            got = coef[d].cpu().numpy()
+            # cond(A) ~ 2.7e8 at T = 0.2 (SURVEY §6): normwise 1e-9 still holds for both solvers
+            assert (np.abs(got - ref).max(axis=(0, 2)) / np.abs(ref).max(axis=(0, 2))).max() <= 1e-9, (solver, d)
+            ref_pos = mo.sample_trajectory(ref, rdur, ts)
+            assert np.abs(pos[d] - ref_pos).max() <= 1e-9 * max(1.0, np.abs(ref_pos).max()), (solver, d)
+        packed = mst.pack_pol_matrix(coef, dur).cpu().numpy()
+        assert packed.shape == (3, 49, 33) and packed.dtype == np.float32
+        for d, mat in ((0, m1), (1, m2)):
+            ours = mst.sample_batch(packed[d][None, :, 1:].reshape(1, 49, 4, 8).astype(np.float64),
+                                    packed[d][None, :, 0].astype(np.float64), ts=ts).cpu().numpy()[0]
+            theirs = mst.sample_batch(mat[None, :, 1:].reshape(1, 49, 4, 8), mat[None, :, 0], ts=ts).cpu().numpy()[0]
+            assert np.abs(ours[:, :3] - theirs[:, :3]).max() < 5e-6, (solver, d)
+    # the planned rigid-body states are collision-free for the 3-drone robot mesh (FCL accepted them)
+    robot, env = mst.Mesh(_soup("custom_triangle_robot")), mst.Mesh(_soup("env-scene-ltu-experiment"))
+    assert int(mst.collide_poses(robot, env, rb[0]).sum()) == 0
+    # and the whole formation trajectory, sampled: pipeline on the rigid body's own trajectory
+    res = mst.pipeline(rb, t[None], 100, robot, env)
+    assert int(res.info[0]) == 0 and int(res.any_hit[0]) == 0
+
+
 def test_config2_formations_4096x5():
     """4,096 formations x 5 drones x 10 pieces x 3 axes: one time vector per formation."""
     from oracle import minsnap_oracle as mo

@@ -4,6 +4,9 @@
   ncu -i X.ncu-rep --page source --print-source cuda,sass --csv > src.csv
   python tools/ncu_summary.py counters raw.csv            > profiles/..._ncu.txt
   python tools/ncu_summary.py lines src.csv KERNEL [N]    > profiles/..._hot_lines.txt
+  python tools/ncu_summary.py json raw.csv KERNEL TRAJECTORIES > profiles/r2_onepass_counters.json
+      (per-trajectory DRAM bytes and executed FP64 instructions of KERNEL: what bench.py reads for
+       roofline.traffic and the FP64 fraction)
 """
 import csv, sys, collections
 
@@ -25,7 +28,64 @@ COUNTERS = [
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum",
+    "smsp__inst_executed_op_shared_st.sum",
 ]
+
+
+def _num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return None
+
+
+def as_json(path, kernel, trajectories):
+    import json
+    rows = list(csv.reader(open(path)))
+    head, units = rows[0], rows[1]
+    for row in rows[2:]:
+        if kernel not in row[head.index("Kernel Name")]:
+            continue
+
+        def get(name, scale=True):
+            if name not in head:
+                return None
+            i = head.index(name)
+            v = _num(row[i])
+            if v is None:
+                return None
+            u = units[i].lower()
+            if scale and u.startswith("mbyte"):
+                v *= 1e6
+            elif scale and u.startswith("gbyte"):
+                v *= 1e9
+            elif scale and u.startswith("kbyte"):
+                v *= 1e3
+            return v
+        dram = (get("dram__bytes_read.sum") or 0.0) + (get("dram__bytes_write.sum") or 0.0)
+        dfma = get("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum")
+        dmul = get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum")
+        dadd = get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
+        out = {"kernel": row[head.index("Kernel Name")][:80], "trajectories_per_launch": trajectories,
+               "gpu_time_us": get("gpu__time_duration.sum", scale=False),
+               "dram_bytes_per_trajectory": dram / trajectories,
+               "dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"),
+               "warp_instructions_per_trajectory": (get("smsp__inst_executed.sum") or 0.0) / trajectories,
+               "source": "ncu --set full --clock-control none (cold-cache, serialised replays)"}
+        if None not in (dfma, dmul, dadd):
+            out["fp64_instructions_per_trajectory"] = (dfma + dmul + dadd) / trajectories
+            out["fp64_flops_per_trajectory"] = (2 * dfma + dmul + dadd) / trajectories
+        print(json.dumps(out, indent=1))
+        return
+    raise SystemExit("kernel %s not in %s" % (kernel, path))
+
 
 
 def counters(path):
@@ -72,5 +132,7 @@ def lines(path, kernel, top=40):
 if __name__ == "__main__":
     if sys.argv[1] == "counters":
         counters(sys.argv[2])
+    elif sys.argv[1] == "json":
+        as_json(sys.argv[2], sys.argv[3], int(sys.argv[4]))
     else:
         lines(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40)
