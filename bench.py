@@ -241,14 +241,14 @@ class ClockSampler(threading.Thread):
 
 # --------------------------------------------------------------------------- GPU arm
 def load_profile_counters():
-    """Per-trajectory counters of the dominant kernel from the tracked ncu capture
-    (profiles/r2_onepass_counters.json, written by tools/ncu_summary.py from the .ncu-rep of this
-    same command): DRAM bytes and executed FP64 instructions.  None when the file is absent."""
+    """Per-trajectory counters of the pipeline's kernels from the tracked ncu capture
+    (profiles/r2_kernel_counters.json, written by tools/ncu_summary.py from the .ncu-rep of this same
+    command): DRAM bytes and executed FP64 instructions per kernel.  {} when the file is absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r2_onepass_counters.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_kernel_counters.json")) as fh:
             return json.load(fh)
     except Exception:
-        return None
+        return {}
 
 
 def run_ours(args):
@@ -410,10 +410,16 @@ def run_ours(args):
     ws = torch.empty((max(1, lib.mst_pipeline_workspace_bytes(B, N_SEG, K_AX, 1, S_SAMPLES)),), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
-    def pipeline_only():
-        _abi.check(lib.mst_pipeline(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES, robot.handle,
+    def pipeline_call(solver):
+        _abi.check(lib.mst_pipeline(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, solver, S_SAMPLES, robot.handle,
                                     env.handle, res.coef.data_ptr(), res.dur.data_ptr(), res.info.data_ptr(),
                                     res.hit.data_ptr(), res.any_hit.data_ptr(), ws.data_ptr(), st), "mst_pipeline")
+
+    def pipeline_only():
+        pipeline_call(_abi.SOLVER_AUTO)
+
+    def onepass_only():
+        pipeline_call(_abi.SOLVER_AUTO_ONE_PASS)
 
     def solve_only():
         _abi.check(lib.mst_solve_batch(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO,
@@ -424,11 +430,12 @@ def run_ours(args):
         _abi.check(lib.mst_collide_trajectories(res.coef.data_ptr(), res.dur.data_ptr(), B, N_SEG, K_AX, S_SAMPLES,
                                                 robot.handle, env.handle, res.hit.data_ptr(), res.any_hit.data_ptr(),
                                                 st), "mst_collide_trajectories")
-    pipeline_only(); solve_only(); collide_only()
+    pipeline_only(); onepass_only(); solve_only(); collide_only()
     side = max(3, args.steps // 2)
-    stage_ms["onepass_kernel (+ list-mode banded_lu / sample_collide, empty list)"] = timed(pipeline_only, side) / side
-    stage_ms["two-launch reference: condensed_cols_kernel"] = timed(solve_only, side) / side
-    stage_ms["two-launch reference: sample_collide_kernel"] = timed(collide_only, side) / side
+    stage_ms["pipeline, two launches (default): condensed_cols_kernel + sample_collide_kernel"] = timed(pipeline_only, side) / side
+    stage_ms["condensed_cols_kernel (+ banded_lu_kernel on the empty declined list)"] = timed(solve_only, side) / side
+    stage_ms["sample_collide_kernel"] = timed(collide_only, side) / side
+    stage_ms["pipeline, single pass (MST_SOLVER_AUTO_ONE_PASS): onepass_kernel"] = timed(onepass_only, side) / side
 
     peaks = {}
     try:
@@ -438,12 +445,17 @@ def run_ours(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # dominant kernel: onepass_kernel = the whole step.  Compulsory bytes per trajectory:
-    # waypoints + stamps in, coefficients + flags out = ALG_BYTES.
-    dom_ms = stage_ms["onepass_kernel (+ list-mode banded_lu / sample_collide, empty list)"]
-    achieved = B * ALG_BYTES / (dom_ms * 1e-3) / 1e9
+    # dominant kernel: sample_collide_kernel.  Its compulsory bytes per trajectory: coefficients and
+    # durations in, per-sample flags + any-flag out; the whole step is reported beside it
+    # against SURVEY §8d's ALG_BYTES.
+    dom_ms = stage_ms["sample_collide_kernel"]
+    step_ms = stage_ms["pipeline, two launches (default): condensed_cols_kernel + sample_collide_kernel"]
+    one_ms = stage_ms["pipeline, single pass (MST_SOLVER_AUTO_ONE_PASS): onepass_kernel"]
+    dom_bytes = N_SEG * K_AX * 64 + N_SEG * 8 + S_SAMPLES + 1
+    achieved = B * dom_bytes / (dom_ms * 1e-3) / 1e9
     counters = load_profile_counters()
-    traffic = counters["dram_bytes_per_trajectory"] * B if counters else None
+    c_dom, c_sol, c_one = (counters.get(k) for k in ("sample_collide_kernel", "condensed_cols_kernel", "onepass_kernel"))
+    traffic = c_dom["dram_bytes_per_trajectory"] * B if c_dom else None
     # FP64 roof: measured in this run (tools/fp64_peak.py)
     fp64 = None
     try:
@@ -452,7 +464,7 @@ def run_ours(args):
         fp64 = fp64_peak.measure()
     except Exception as exc:  # the probe library did not travel
         sys.stderr.write("fp64 peak probe unavailable: %r\n" % (exc,))
-    traj_per_s = B / (dom_ms * 1e-3)
+    traj_per_s = B / (step_ms * 1e-3)
     fp64_block = None
     if fp64:
         peak_tf = fp64["fp64_fma_tflops"]
@@ -461,13 +473,13 @@ def run_ours(args):
                       # SURVEY §8d's credited flops (banded-LU formulation of the reference's own system)
                       "credited_flops_per_trajectory": 45600,
                       "fp64_frac_credited": traj_per_s * 45600 / (peak_tf * 1e12)}
-        if counters and counters.get("fp64_flops_per_trajectory"):
-            ex = counters["fp64_flops_per_trajectory"]
+        if c_dom and c_sol and c_dom.get("fp64_flops_per_trajectory") and c_sol.get("fp64_flops_per_trajectory"):
+            ex = c_dom["fp64_flops_per_trajectory"] + c_sol["fp64_flops_per_trajectory"]
+            ins = c_dom["fp64_instructions_per_trajectory"] + c_sol["fp64_instructions_per_trajectory"]
             fp64_block.update({"executed_flops_per_trajectory": ex, "fp64_frac": traj_per_s * ex / (peak_tf * 1e12),
-                               "executed_fp64_instructions_per_trajectory": counters.get("fp64_instructions_per_trajectory"),
-                               "fp64_pipe_frac": (traj_per_s * counters["fp64_instructions_per_trajectory"] /
-                                                  fp64["fma"]["thread_instructions_per_s"])
-                               if counters.get("fp64_instructions_per_trajectory") else None})
+                               "executed_fp64_instructions_per_trajectory": ins,
+                               "fp64_pipe_frac": traj_per_s * ins / fp64["fma"]["thread_instructions_per_s"],
+                               "fp64_note": "whole step (both kernels), executed flops from the tracked ncu capture"})
 
     # ---- end to end through HOST buffers (pinned), copies inside the timed region ----------
     hp = HostPipeline(N_SEG, K_AX, S_SAMPLES, robot, env, chunk=args.e2e_chunk)
@@ -498,10 +510,21 @@ def run_ours(args):
         launches_per_step += 1      # wire patch kernel (list mode) behind mst_pipeline_wire
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "hbm_frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "onepass_kernel<3> (the whole step: solve + sample + collide in one launch)",
-                "alg_bytes_per_trajectory": ALG_BYTES, "trajectories_per_launch": B, "kernel_ms": dom_ms,
+                "kernel": "sample_collide_kernel<3> (%.0f %% of the two-launch step)" % (100 * dom_ms / step_ms),
+                "alg_bytes_per_trajectory": dom_bytes, "trajectories_per_launch": B, "kernel_ms": dom_ms,
                 "kernels_ms": stage_ms,
-                "traffic_source": "profiles/r2_onepass_counters.json (ncu --set full of this command)" if counters else None,
+                "traffic_source": "profiles/r2_kernel_counters.json (ncu --set full of this command)" if c_dom else None,
+                "whole_step": {"alg_bytes_per_trajectory": ALG_BYTES, "ms": step_ms,
+                               "achieved_gbs": B * ALG_BYTES / (step_ms * 1e-3) / 1e9,
+                               "hbm_frac": B * ALG_BYTES / (step_ms * 1e-3) / 1e9 / peak_gbs,
+                               "traffic": (c_dom["dram_bytes_per_trajectory"] + c_sol["dram_bytes_per_trajectory"]) * B
+                               if c_dom and c_sol else None},
+                "single_pass": {"kernel": "onepass_kernel<3>", "ms": one_ms, "alg_bytes_per_trajectory": ALG_BYTES,
+                                "achieved_gbs": B * ALG_BYTES / (one_ms * 1e-3) / 1e9,
+                                "hbm_frac": B * ALG_BYTES / (one_ms * 1e-3) / 1e9 / peak_gbs,
+                                "traffic": c_one["dram_bytes_per_trajectory"] * B if c_one else None,
+                                "note": "coefficients reach HBM once; slower than the two launches on B200 (10 resident "
+                                        "warps per SM against 14-16), so not the default: profiles/r2_onepass_history.md"},
                 "note": "instruction/latency bound (branchy FP64 geometry, short recurrences), not bandwidth bound: "
                         "both fractions are reported, see profiles/"}
     if fp64_block:
@@ -516,7 +539,7 @@ def run_ours(args):
                    "trajectories_per_gpu": B, "l2": "inputs+outputs %.2f GB per step >> 126 MB L2 (no flush needed)"
                    % (B * (ALG_BYTES + N_SEG * 8 + 4) / 1e9),
                    "gather": gather_note,
-                   "solver": "auto (condensed LDL^T inside the single-pass kernel; banded pivoted LU for wide duration spreads)"},
+                   "solver": "auto (condensed LDL^T; banded pivoted LU for wide duration spreads)"},
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),

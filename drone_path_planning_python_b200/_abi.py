@@ -75,7 +75,7 @@ PROTOTYPES["mst_pipeline_wire"] = (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_i
                                                   c_void_p])
 
 MST_OK = 0
-SOLVER_AUTO, SOLVER_BANDED_LU, SOLVER_CONDENSED = 0, 1, 2
+SOLVER_AUTO, SOLVER_BANDED_LU, SOLVER_CONDENSED, SOLVER_AUTO_ONE_PASS = 0, 1, 2, 3
 SAMPLE_PIECEWISE, SAMPLE_TRAJECTORY = 0, 1
 INFO_DECREASING, INFO_NONFINITE, INFO_DECLINED = -1, -2, -3
 

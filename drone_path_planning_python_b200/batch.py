@@ -19,7 +19,8 @@ import torch
 
 from . import _abi
 
-_SOLVERS = {"auto": _abi.SOLVER_AUTO, "banded_lu": _abi.SOLVER_BANDED_LU, "condensed": _abi.SOLVER_CONDENSED}
+_SOLVERS = {"auto": _abi.SOLVER_AUTO, "banded_lu": _abi.SOLVER_BANDED_LU, "condensed": _abi.SOLVER_CONDENSED,
+            "auto_one_pass": _abi.SOLVER_AUTO_ONE_PASS}   # the last one: pipeline() only
 _MODES = {"piecewise": _abi.SAMPLE_PIECEWISE, "trajectory": _abi.SAMPLE_TRAJECTORY}
 
 

@@ -82,10 +82,13 @@ int launch_wire_patch(const double* coef, const double* dur, const uint8_t* hit,
                       int G, int S, const int* list, const int* list_count, const WireTargets* wire,
                       cudaStream_t stream);
 
-// MST_PIPELINE_TWO_PASS=1 forces the two-launch pipeline (solver kernel, then sample+collide kernel)
-static bool two_pass_forced() {
-  static const bool forced = getenv("MST_PIPELINE_TWO_PASS") != nullptr && atoi(getenv("MST_PIPELINE_TWO_PASS")) != 0;
-  return forced;
+// Which pipeline mst_pipeline(MST_SOLVER_AUTO) runs: the two-launch one by default — measured faster
+// on B200 (3.4 ms against 4.2 ms per 1 M trajectories: the single-pass kernel keeps 10 warps per SM
+// resident instead of 14-16, profiles/r2_onepass_history.md); MST_PIPELINE_ONE_PASS=1 switches the
+// default.  MST_SOLVER_AUTO_ONE_PASS always asks for the single-pass kernel, mst_pipeline_wire needs it.
+static bool one_pass_default() {
+  static const bool on = getenv("MST_PIPELINE_ONE_PASS") != nullptr && atoi(getenv("MST_PIPELINE_ONE_PASS")) != 0;
+  return on;
 }
 
 // Trajectories per pass of the pipeline (solver launch + fused sample/collide launch).
@@ -262,8 +265,9 @@ extern "C" size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_ti
 
 // does the single-pass kernel take these sizes?  (mirrors launch_onepass's own checks, minus the meshes)
 static bool onepass_sizes(int n, int K, int G, int solver, int S) {
-  return !two_pass_forced() && solver == MST_SOLVER_AUTO && (K == 3 || K == 4) && G * K <= 32 && n >= 2 && n <= 32 &&
-         S >= 32 && S <= 4096 && banded_lu_smem_per_warp(n, G * K) <= MST_MAX_SMEM;
+  const bool wanted = solver == MST_SOLVER_AUTO_ONE_PASS || (solver == MST_SOLVER_AUTO && one_pass_default());
+  return wanted && (K == 3 || K == 4) && G * K <= 32 && n >= 2 && n <= 32 && S >= 32 && S <= 4096 &&
+         banded_lu_smem_per_warp(n, G * K) <= MST_MAX_SMEM;
 }
 
 extern "C" int mst_pipeline_launch_count(int B, int n, int K, int share_time_group, int solver, int S) {
@@ -273,7 +277,7 @@ extern "C" int mst_pipeline_launch_count(int B, int n, int K, int share_time_gro
   // single pass: the fused kernel + the two list-mode kernels behind it (pivoted solver, sampling of
   // its groups; both exit at once when no group was handed over)
   if (onepass_sizes(n, K, share_time_group, solver, S)) return chunks * 3;
-  const int solve = solver == MST_SOLVER_AUTO ? 2 : 1;  // condensed (+ banded LU over the declined list)
+  const int solve = (solver == MST_SOLVER_AUTO || solver == MST_SOLVER_AUTO_ONE_PASS) ? 2 : 1;  // condensed (+ banded LU over the declined list)
   return chunks * (solve + 1);                           // + fused sample/collide/any-hit
 }
 
@@ -313,7 +317,8 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
       if (rc != MST_ERR_TOO_LARGE) return rc;
     }
     if (wire) return MST_ERR_TOO_LARGE;   // the two-launch pipeline has no wire outputs
-    rc = mst_solve_batch(wc, tc, nb, n, K, G, solver, cc, dd, info + b0, workspace, stream);
+    rc = mst_solve_batch(wc, tc, nb, n, K, G, solver == MST_SOLVER_AUTO_ONE_PASS ? MST_SOLVER_AUTO : solver, cc, dd,
+                         info + b0, workspace, stream);
     if (rc != MST_OK) return rc;
     rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st);
     if (rc != MST_OK) return rc;
@@ -328,7 +333,8 @@ extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int
   const int G = share_time_group;
   if (S < 1 || (K != 3 && K != 4) || !robot || !env || G < 1 || B < 0 || n < 1 || B % G != 0)
     return MST_ERR_INVALID;
-  if (solver != MST_SOLVER_AUTO && solver != MST_SOLVER_BANDED_LU && solver != MST_SOLVER_CONDENSED)
+  if (solver != MST_SOLVER_AUTO && solver != MST_SOLVER_BANDED_LU && solver != MST_SOLVER_CONDENSED &&
+      solver != MST_SOLVER_AUTO_ONE_PASS)
     return MST_ERR_INVALID;
   if (B == 0) return MST_OK;
   if (!hit || !any_hit || !workspace || !wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
@@ -355,6 +361,6 @@ extern "C" int mst_pipeline_wire(const double* wp, const double* t, int B, int n
     w.any[i] = wire->any_hit ? wire->any_hit[i] : nullptr;
     if ((w.hit[i] == nullptr) != (w.any[i] == nullptr)) return MST_ERR_INVALID;
   }
-  return pipeline_impl(wp, t, B, n, K, G, MST_SOLVER_AUTO, S, robot, env, coef, dur, info, hit, any_hit, &w, workspace,
-                       stream);
+  return pipeline_impl(wp, t, B, n, K, G, MST_SOLVER_AUTO_ONE_PASS, S, robot, env, coef, dur, info, hit, any_hit, &w,
+                       workspace, stream);
 }

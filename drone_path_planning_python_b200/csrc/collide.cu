@@ -21,7 +21,9 @@
 namespace mst {
 
 // POSE 0: pose = (x,y,z), identity rotation; 1: (x,y,z,yaw); 2: (x,y,z,qx,qy,qz,qw)
-template <int POSE>
+// GLOBAL = true: the mesh images stay in device memory (environments / robots too large to stage);
+// the cursor engine then walks the block boxes first, and no plane x vertex table exists.
+template <int POSE, bool GLOBAL>
 __global__ void __launch_bounds__(128, 4)
 collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
                const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
@@ -32,12 +34,12 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
   __shared__ __align__(8) unsigned long long bar;
   __shared__ PoseRing<NP> rings[4];
   PoseRing<NP>& ring = rings[threadIdx.x >> 5];
-  stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
-  const MeshView rb = mesh_view(smem_raw, rl);
-  const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
+  if (!GLOBAL) stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
+  const MeshView rb = GLOBAL ? mesh_view(robot_img, rl) : mesh_view(smem_raw, rl);
+  const MeshView ev = GLOBAL ? mesh_view(env_img, el) : mesh_view(smem_raw + rl.bytes, el);
   const bool engine = collide_engine_supports(rb, ev);
-  double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);  // plane x vertex table
-  if (engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
+  double* nv = GLOBAL ? nullptr : reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);  // plane x vertex table
+  if (!GLOBAL && engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
   __syncthreads();
   unsigned ring_head = 0u, ring_tail = 0u;  // warp-uniform
   auto report = [&](int hi32, int lo32, bool h) {
@@ -61,10 +63,10 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
     const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
     if (active && !near) hit[idx] = 0;
     ring_push<POSE>(ring, ring_tail, near, pp, (int)(idx >> 32), (int)(idx & 0xffffffffll), -1, 0u, 0u);
-    while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
+    while (ring_tail - ring_head >= 32u) ring_drain<POSE, !GLOBAL>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
   }
   while (ring_tail != ring_head)
-    ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
+    ring_drain<POSE, !GLOBAL>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
 // Motion validation for a sampling planner: states (x, y, z, yaw) interpolated linearly between
@@ -73,6 +75,7 @@ collide_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb
 // RB_planning_sep_coll_check.py:79), every interpolated state collision-checked like
 // isStateValid does (:208-215).  invalid[m] = 1 iff some state collides.  invalid[] must be
 // zeroed by the caller (the launcher does it).
+template <bool GLOBAL>
 __global__ void __launch_bounds__(128, 4)
 collide_motions_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
                        const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
@@ -83,9 +86,9 @@ collide_motions_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBo
   __shared__ __align__(8) unsigned long long bar;
   __shared__ PoseRing<NP> rings[4];
   PoseRing<NP>& ring = rings[threadIdx.x >> 5];
-  stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
-  const MeshView rb = mesh_view(smem_raw, rl);
-  const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
+  if (!GLOBAL) stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
+  const MeshView rb = GLOBAL ? mesh_view(robot_img, rl) : mesh_view(smem_raw, rl);
+  const MeshView ev = GLOBAL ? mesh_view(env_img, el) : mesh_view(smem_raw + rl.bytes, el);
   const bool engine = collide_engine_supports(rb, ev);
   const double* nv = nullptr;
   unsigned ring_head = 0u, ring_tail = 0u;
@@ -115,10 +118,10 @@ collide_motions_kernel(const void* __restrict__ robot_img, MeshLayout rl, MeshBo
     }
     const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
     ring_push<POSE>(ring, ring_tail, near, pp, (int)(m >> 32), (int)(m & 0xffffffffll), -1, 0u, 0u);
-    while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
+    while (ring_tail - ring_head >= 32u) ring_drain<POSE, !GLOBAL>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
   }
   while (ring_tail != ring_head)
-    ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
+    ring_drain<POSE, !GLOBAL>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -157,15 +160,18 @@ int launch_collide_motions(const mst_mesh* robot, const mst_mesh* env, const dou
   if (M == 0) return MST_OK;
   cudaError_t e = cudaMemsetAsync(invalid, 0, (size_t)M, stream);
   if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
-  const size_t smem = robot->layout.bytes + env->layout.bytes;
+  size_t smem = robot->layout.bytes + env->layout.bytes;
+  const bool global = smem > MST_STAGE_LIMIT;   // large meshes are read in place (block boxes cull)
+  if (global) smem = 0;
+  auto kern = global ? collide_motions_kernel<true> : collide_motions_kernel<false>;
   {
-    const int rc = allow_dynamic_smem((const void*)collide_motions_kernel, smem);
+    const int rc = allow_dynamic_smem((const void*)kern, smem);
     if (rc != MST_OK) return rc;
   }
   long long blocks = (M * steps + 127) / 128;
   const long long cap = (long long)MST_SM_COUNT * 4;
   if (blocks > cap) blocks = cap;
-  collide_motions_kernel<<<(unsigned)blocks, 128, smem, stream>>>(robot->d_image, robot->layout, robot->bounds,
+  kern<<<(unsigned)blocks, 128, smem, stream>>>(robot->d_image, robot->layout, robot->bounds,
                                                                   env->d_image, env->layout, env->bounds, a, b, M,
                                                                   steps, invalid);
   return check_launch();
@@ -175,10 +181,14 @@ int launch_collide(const mst_mesh* robot, const mst_mesh* env, const double* pos
                    int pose_dim, uint8_t* hit, cudaStream_t stream) {
   if (P == 0) return MST_OK;
   // the plane x vertex table serves translation-only poses alone
-  const size_t smem = robot->layout.bytes + env->layout.bytes +
-                      (pose_dim == 3 ? sizeof(double) * collide_table_doubles(env->T, robot->V) : 0);
+  size_t smem = robot->layout.bytes + env->layout.bytes +
+                (pose_dim == 3 ? sizeof(double) * collide_table_doubles(env->T, robot->V) : 0);
+  const bool global = smem > MST_STAGE_LIMIT;   // large meshes are read in place (block boxes cull)
+  if (global) smem = 0;
   void (*kern)(const void*, MeshLayout, MeshBounds, const void*, MeshLayout, MeshBounds, const double*, long long,
-               uint8_t*) = pose_dim == 3 ? collide_kernel<0> : (pose_dim == 4 ? collide_kernel<1> : collide_kernel<2>);
+               uint8_t*);
+  if (global) kern = pose_dim == 3 ? collide_kernel<0, true> : (pose_dim == 4 ? collide_kernel<1, true> : collide_kernel<2, true>);
+  else kern = pose_dim == 3 ? collide_kernel<0, false> : (pose_dim == 4 ? collide_kernel<1, false> : collide_kernel<2, false>);
   {
     const int rc = allow_dynamic_smem((const void*)kern, smem);
     if (rc != MST_OK) return rc;

@@ -314,9 +314,10 @@ __host__ __device__ inline bool robot_hits_env_culled(const double* R, const dou
 // all pairs: stopping early only skips pairs after a hit.
 //
 // POSE: 0 translation (x,y,z); 1 yaw (x,y,z,sin(yaw/2),cos(yaw/2)); 2 quaternion
-// (x,y,z,qx,qy,qz,qw).  nv (POSE 0 only): tables n_e . v and m_ek . v of the env planes and edge
-// planes against the robot's unique vertices (build_plane_vertex_table) — a translation leaves
-// them constant, so the signed distance of vertex v to a plane is one add.
+// (x,y,z,qx,qy,qz,qw).  nv (POSE 0 only; may be null): tables n_e . v and m_ek . v of the env planes
+// and edge planes against the robot's unique vertices (build_plane_vertex_table) — a translation
+// leaves them constant, so the signed distance of vertex v to a plane is one add.  Without the
+// table (environments too large for shared memory) the general form runs with R = identity.
 constexpr int COLLIDE_MAX_V = 32;    // unique robot vertices the bit masks can hold
 constexpr int COLLIDE_MAX_TR = 32;   // robot triangles the cursor's bit mask can hold
 constexpr int COLLIDE_RING = 64;     // poses per warp ring (a power of two, >= 2 * 32)
@@ -430,7 +431,9 @@ __device__ __forceinline__ void ring_push(PoseRing<PoseDim<POSE>::N>& ring, unsi
 
 // test up to COLLIDE_ROUNDS candidates for each of the first `count` waiting poses; decided
 // poses are handed to report(id0, id1, hit), the others return to the tail with their cursor
-template <int POSE, class Report>
+// TABLE (POSE 0 only): nv holds the plane x vertex table; false = no table (mesh images read in place
+// from device memory), the general form then runs with R = identity.
+template <int POSE, bool TABLE = true, class Report>
 __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, unsigned& head, unsigned& tail, int count,
                                            const MeshView& rb, const MeshBounds& rbb, const MeshView& ev,
                                            const double* nv, Report&& report) {
@@ -447,7 +450,7 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
   __syncwarp();  // entries are in registers: the slots may be reused by the re-queue below
   head += (unsigned)count;
 
-  double R[9], lo[3], hi[3];
+  double R[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0}, lo[3], hi[3];
   pose_rotation<POSE>(pp, R);
   robot_world_box<POSE>(pp, R, rbb, lo, hi);
   const float flo0 = round_down_f(lo[0]), flo1 = round_down_f(lo[1]), flo2 = round_down_f(lo[2]);
@@ -484,12 +487,22 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
             // single precision with every bound rounded outward: a box pair that meets in double
             // precision meets here too (the plane and pair tests that follow are the exact ones)
             const int cnt = min(32, ev.T - base);
-            const float4* fb = reinterpret_cast<const float4*>(ev.fbox) + 2 * base;
+            // meshes of more than one block: the block's own box first (the level above the triangle
+            // boxes; blocks are compact because the triangles are stored in Morton order)
+            bool block_near = true;
+            if (ev.T > 32) {
+              const float4* bb = reinterpret_cast<const float4*>(ev.bbox) + 2 * (base >> 5);
+              const float4 b0 = bb[0], b1 = bb[1];
+              block_near = !(fhi0 < b0.x || flo0 > b0.w || fhi1 < b0.y || flo1 > b1.x || fhi2 < b0.z || flo2 > b1.y);
+            }
+            if (block_near) {
+              const float4* fb = reinterpret_cast<const float4*>(ev.fbox) + 2 * base;
 #pragma unroll 4
-            for (int i = 0; i < cnt; ++i) {
-              const float4 b0 = fb[2 * i], b1 = fb[2 * i + 1];  // min x y z, max x | max y z, pad
-              emask |= (unsigned)(!(fhi0 < b0.x || flo0 > b0.w || fhi1 < b0.y || flo1 > b1.x || fhi2 < b0.z ||
-                                    flo2 > b1.y)) << i;
+              for (int i = 0; i < cnt; ++i) {
+                const float4 b0 = fb[2 * i], b1 = fb[2 * i + 1];  // min x y z, max x | max y z, pad
+                emask |= (unsigned)(!(fhi0 < b0.x || flo0 > b0.w || fhi1 < b0.y || flo1 > b1.x || fhi2 < b0.z ||
+                                      flo2 > b1.y)) << i;
+              }
             }
             e = base + 31;  // nothing of this block consumed yet; (e >> 5) names the block
           }
@@ -508,7 +521,7 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
           const double o0 = ed[0] * pp[0] + ed[1] * pp[1] + ed[2] * pp[2] - ed[3];
           const double o1 = ed[4] * pp[0] + ed[5] * pp[1] + ed[6] * pp[2] - ed[7];
           const double o2 = ed[8] * pp[0] + ed[9] * pp[1] + ed[10] * pp[2] - ed[11];
-          if (POSE == 0) {
+          if (POSE == 0 && TABLE) {
             const double* row = nv + (size_t)e * COLLIDE_TABLE_ROWS * rb.V;
             for (int v = 0; v < rb.V; ++v) {
               const double dist = row[v] + off;

@@ -9,12 +9,61 @@
 
 namespace mst {
 
+// 30-bit Morton code of a point in the unit cube (10 bits per axis)
+inline unsigned morton3(double x, double y, double z) {
+  auto spread = [](double v) -> unsigned {
+    double s = v * 1024.0;
+    unsigned q = s <= 0.0 ? 0u : (s >= 1023.0 ? 1023u : (unsigned)s);
+    q = (q | (q << 16)) & 0x030000FFu;
+    q = (q | (q << 8)) & 0x0300F00Fu;
+    q = (q | (q << 4)) & 0x030C30C3u;
+    q = (q | (q << 2)) & 0x09249249u;
+    return q;
+  };
+  return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+
 // returns a malloc'ed image of layout->bytes (>= 16) bytes, or NULL when out of memory
-inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, MeshBounds* bounds) {
+inline void* build_mesh_image(const double* tri_in, int T, MeshLayout* layout, MeshBounds* bounds) {
   const size_t nt = (size_t)(T > 0 ? T : 1);
+  // Triangles are stored in Morton order of their centroids when there is more than one block of 32:
+  // the blocks the collision cursor walks are then spatially compact and their boxes (bbox) cull
+  // well.  A collision answer does not depend on the order (any intersecting pair is a hit).
+  double* sorted = (double*)malloc(sizeof(double) * 9 * nt);
+  if (!sorted) return NULL;
+  memcpy(sorted, tri_in, sizeof(double) * 9 * (size_t)T);
+  if (T > 32) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < 3 * T; ++c)
+      for (int k = 0; k < 3; ++k) {
+        const double v = tri_in[3 * c + k];
+        if (v < lo[k]) lo[k] = v;
+        if (v > hi[k]) hi[k] = v;
+      }
+    struct Key { unsigned code; int t; };
+    Key* keys = (Key*)malloc(sizeof(Key) * nt);
+    if (!keys) { free(sorted); return NULL; }
+    for (int t = 0; t < T; ++t) {
+      double c[3];
+      for (int k = 0; k < 3; ++k) {
+        const double m = (tri_in[9 * t + k] + tri_in[9 * t + 3 + k] + tri_in[9 * t + 6 + k]) / 3.0;
+        c[k] = hi[k] > lo[k] ? (m - lo[k]) / (hi[k] - lo[k]) : 0.0;
+      }
+      keys[t].code = morton3(c[0], c[1], c[2]);
+      keys[t].t = t;
+    }
+    qsort(keys, (size_t)T, sizeof(Key), [](const void* a, const void* b) -> int {
+      const Key* x = (const Key*)a; const Key* y = (const Key*)b;
+      if (x->code != y->code) return x->code < y->code ? -1 : 1;
+      return x->t < y->t ? -1 : (x->t > y->t ? 1 : 0);
+    });
+    for (int t = 0; t < T; ++t) memcpy(sorted + 9 * (size_t)t, tri_in + 9 * (size_t)keys[t].t, sizeof(double) * 9);
+    free(keys);
+  }
+  const double* tri = sorted;
   int* idx = (int*)malloc(sizeof(int) * 3 * nt);
   double* uv = (double*)malloc(sizeof(double) * 9 * nt);
-  if (!idx || !uv) { free(idx); free(uv); return NULL; }
+  if (!idx || !uv) { free(idx); free(uv); free(sorted); return NULL; }
   // unique vertices by exact equality (what the reference's indexed triangles are built on,
   // src/RigidBodyPlanners/fcl_checker.py:28-40)
   int V = 0;
@@ -28,7 +77,7 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
   }
   *layout = mesh_layout(T, V);
   char* base = (char*)calloc(1, layout->bytes > 0 ? layout->bytes : 16);
-  if (!base) { free(idx); free(uv); return NULL; }
+  if (!base) { free(idx); free(uv); free(sorted); return NULL; }
   double* itri = (double*)base;
   double* ibox = (double*)(base + layout->off_box);
   double* ipl = (double*)(base + layout->off_plane);
@@ -38,6 +87,9 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
   unsigned* ivtri = (unsigned*)(base + layout->off_vtri);
   float* ifbox = (float*)(base + layout->off_fbox);
   double* iedge = (double*)(base + layout->off_edge);
+  float* ibbox = (float*)(base + layout->off_bbox);
+  for (int b = 0; b < (T + 31) / 32; ++b)
+    for (int k = 0; k < 3; ++k) { ibbox[8 * b + k] = INFINITY; ibbox[8 * b + 3 + k] = -INFINITY; }
   for (int t = 0; t < T && t < 32; ++t)
     for (int c = 0; c < 3; ++c) ivtri[idx[3 * t + c]] |= 1u << t;
   memcpy(itri, tri, sizeof(double) * 9 * (size_t)T);
@@ -69,6 +121,9 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
       if ((double)hi < box[3 + k]) hi = nextafterf(hi, INFINITY);
       ifbox[8 * t + k] = lo;
       ifbox[8 * t + 3 + k] = hi;
+      float* bb = ibbox + 8 * (t / 32);
+      if (lo < bb[k]) bb[k] = lo;
+      if (hi > bb[3 + k]) bb[3 + k] = hi;
     }
     for (int k = 0; k < 3; ++k) {
       if (box[k] < bounds->root[k]) bounds->root[k] = box[k];
@@ -105,6 +160,7 @@ inline void* build_mesh_image(const double* tri, int T, MeshLayout* layout, Mesh
   }
   free(idx);
   free(uv);
+  free(sorted);
   return base;
 }
 

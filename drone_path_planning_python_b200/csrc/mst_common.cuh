@@ -8,6 +8,9 @@
 #define MST_NCOEF 8
 #define MST_SM_COUNT (mst::sm_count())  // SMs of the current device (148 on B200: 2 dies x 74)
 #define MST_MAX_SMEM (227 * 1024)   // opt-in dynamic shared memory per CTA
+// mesh images (+ plane x vertex table) up to this size are staged into every CTA's shared memory;
+// larger ones are read in place from device memory (4 resident CTAs per SM still fit below it)
+#define MST_STAGE_LIMIT (40 * 1024)
 
 namespace mst {
 
@@ -84,11 +87,14 @@ struct MeshView {
   const float* fbox;               // per triangle, 8 floats: the AABB rounded OUTWARD (min xyz, max xyz, 2 pad)
   const double* edge;              // per triangle, 3 x (mx, my, mz, c): in-plane outward normal of edge k and its
                                    // offset, so that m . x - c > 0 only for points beyond that edge's line
+  const float* bbox;               // per BLOCK of 32 consecutive triangles, 8 floats: the block's box rounded outward
+                                   // (the level above the per-triangle boxes; triangles are stored in Morton order
+                                   // of their centroids, so a block is spatially compact)
 };
 
 struct MeshLayout {
   int T, V;
-  size_t off_box, off_plane, off_vert, off_idx, off_mask, off_vtri, off_fbox, off_edge, bytes;  // byte offsets from base
+  size_t off_box, off_plane, off_vert, off_idx, off_mask, off_vtri, off_fbox, off_edge, off_bbox, bytes;  // byte offsets from base
 };
 
 __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
@@ -106,6 +112,7 @@ __host__ __device__ __forceinline__ MeshLayout mesh_layout(int T, int V) {
   o = (o + 15) & ~(size_t)15;
   L.off_fbox = o;  o += sizeof(float) * 8 * (size_t)T;
   L.off_edge = o;  o += sizeof(double) * 12 * (size_t)T;
+  L.off_bbox = o;  o += sizeof(float) * 8 * (size_t)((T + 31) / 32);
   L.bytes = (o + 15) & ~(size_t)15;
   return L;
 }
@@ -123,6 +130,7 @@ __host__ __device__ __forceinline__ MeshView mesh_view(const void* base, const M
   v.vtri = (const unsigned*)(b + L.off_vtri);
   v.fbox = (const float*)(b + L.off_fbox);
   v.edge = (const double*)(b + L.off_edge);
+  v.bbox = (const float*)(b + L.off_bbox);
   return v;
 }
 

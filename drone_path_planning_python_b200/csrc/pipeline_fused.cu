@@ -44,7 +44,9 @@ constexpr int FUSED_WT_MAX = 32; // trajectories per warp tile (chosen by the la
 // LIST = true: only the trajectories of the time groups in list[0 .. *list_count) are worked on
 // (trajectory j of the launch is list[j / G] * G + j % G) — the groups the single-pass pipeline
 // handed to the pivoted solver; the kernel exits at once when the list is empty.
-template <int K, bool TAB, bool LIST>
+// GLOBAL = true: mesh images read in place from device memory (too large to stage).
+// With both false the code is the round-1 kernel unchanged (every LIST / GLOBAL branch folds away).
+template <int K, bool TAB, bool LIST, bool GLOBAL>
 __global__ void __launch_bounds__(FUSED_THREADS, 4)
 sample_collide_kernel(const double* __restrict__ coef, const double* __restrict__ dur, int B, int n, int S, int FUSED_WT,
                       const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
@@ -65,16 +67,17 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
   __shared__ PoseRing<NP> rings[FUSED_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   PoseRing<NP>& ring = rings[warp];
-  stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
-  const MeshView rb = mesh_view(smem_raw, rl);
-  const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
+  if (!GLOBAL) stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
+  const MeshView rb = GLOBAL ? mesh_view(robot_img, rl) : mesh_view(smem_raw, rl);
+  const MeshView ev = GLOBAL ? mesh_view(env_img, el) : mesh_view(smem_raw + rl.bytes, el);
   const bool engine = collide_engine_supports(rb, ev);
   // behind the meshes: the plane x vertex table, then per-warp tables knots[WT][n+1]
   // (running sums of the durations) and dt[WT]
-  double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
-  if (engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
+  double* nv = GLOBAL ? nullptr : reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
+  if (!GLOBAL && engine && POSE == 0) build_plane_vertex_table(rb, ev, nv);
   __syncthreads();
-  double* tables = nv + ((engine && POSE == 0) ? collide_table_doubles(ev.T, rb.V) : 0);
+  double* tables = GLOBAL ? reinterpret_cast<double*>(smem_raw)
+                          : nv + ((engine && POSE == 0) ? collide_table_doubles(ev.T, rb.V) : 0);
   double* knots = tables + warp * FUSED_WT * (n + 2);
   double* dts = knots + FUSED_WT * (n + 1);
   // thr[WT][n]: first sample index of pieces 1 .. n-1, and (when the launcher found room: TAB)
@@ -105,13 +108,11 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
     const int next_b0 = next_tile < tiles ? (int)(next_tile * FUSED_WT) : B;
     const int next_nb = min(FUSED_WT, B - next_b0);
     {
-      if (!LIST) {
-        const char* dbase = reinterpret_cast<const char*>(dur + (size_t)next_b0 * n);
-        const size_t dbytes = (size_t)max(next_nb, 0) * n * sizeof(double);
+      const char* dbase = reinterpret_cast<const char*>(dur + (size_t)next_b0 * n);
+      const size_t dbytes = LIST ? 0 : (size_t)max(next_nb, 0) * n * sizeof(double);
 #pragma unroll 1
-        for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
-      }
+      for (size_t off = (size_t)lane * 128; off < dbytes; off += 32 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + off));
     }
     // q-th trajectory of this warp counted from the start of the tile; runs on into the next tile
     auto prefetch_trajectory = [&](int q) {
@@ -219,13 +220,15 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
         continue;
       }
       const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
-      if (active && !near) hit[btl * S + s] = 0;
-      ring_push<POSE>(ring, ring_tail, near, pp, (int)btl, s, -1, 0u, 0u);
-      while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
+      if (active && !near) {
+        if (LIST) hit[btl * S + s] = 0; else hit[(size_t)b0 * S + idx] = 0;
+      }
+      ring_push<POSE>(ring, ring_tail, near, pp, LIST ? (int)btl : b0 + tl, s, -1, 0u, 0u);
+      while (ring_tail - ring_head >= 32u) ring_drain<POSE, !GLOBAL>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
     }
   }
   while (ring_tail != ring_head)
-    ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
+    ring_drain<POSE, !GLOBAL>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
 }
 
 // list / list_count (device) non-null: list mode over the time groups of G trajectories named there;
@@ -245,18 +248,24 @@ int launch_sample_collide(const double* coef, const double* dur, int B, int n, i
   const bool tab = n <= 255 && S <= 1024;
   const size_t per_traj = sizeof(double) * (size_t)(n + 2) + sizeof(int) * (size_t)n + (tab ? (size_t)S : 0);
   while (FUSED_WT > 1 && FUSED_WARPS * FUSED_WT * per_traj > 24 * 1024) FUSED_WT /= 2;
-  // the plane x vertex table serves translation-only poses (K = 3) alone
-  const size_t smem = robot->layout.bytes + env->layout.bytes +
-                      (K == 3 ? sizeof(double) * collide_table_doubles(env->T, robot->V) : 0) +
-                      FUSED_WARPS * FUSED_WT * per_traj;
+  // the plane x vertex table serves translation-only poses (K = 3) alone; it exists only when the
+  // robot fits the cursor engine
+  const bool engine = robot->V <= COLLIDE_MAX_V && robot->T <= COLLIDE_MAX_TR;
+  size_t mesh_bytes = robot->layout.bytes + env->layout.bytes +
+                      ((K == 3 && engine) ? sizeof(double) * collide_table_doubles(env->T, robot->V) : 0);
+  const bool global = mesh_bytes > MST_STAGE_LIMIT;   // large meshes are read in place (block boxes cull)
+  if (global) mesh_bytes = 0;
+  const size_t smem = mesh_bytes + FUSED_WARPS * FUSED_WT * per_traj;
   void (*kern)(const double*, const double*, int, int, int, int, const void*, MeshLayout, MeshBounds, const void*,
                MeshLayout, MeshBounds, uint8_t*, uint8_t*, const int*, const int*, int);
+#define MST_PICK(KK, TT, LL) (global ? sample_collide_kernel<KK, TT, LL, true> : sample_collide_kernel<KK, TT, LL, false>)
   if (list)
-    kern = K == 3 ? (tab ? sample_collide_kernel<3, true, true> : sample_collide_kernel<3, false, true>)
-                  : (tab ? sample_collide_kernel<4, true, true> : sample_collide_kernel<4, false, true>);
+    kern = K == 3 ? (tab ? MST_PICK(3, true, true) : MST_PICK(3, false, true))
+                  : (tab ? MST_PICK(4, true, true) : MST_PICK(4, false, true));
   else
-    kern = K == 3 ? (tab ? sample_collide_kernel<3, true, false> : sample_collide_kernel<3, false, false>)
-                  : (tab ? sample_collide_kernel<4, true, false> : sample_collide_kernel<4, false, false>);
+    kern = K == 3 ? (tab ? MST_PICK(3, true, false) : MST_PICK(3, false, false))
+                  : (tab ? MST_PICK(4, true, false) : MST_PICK(4, false, false));
+#undef MST_PICK
   {
     const int rc = allow_dynamic_smem((const void*)kern, smem);
     if (rc != MST_OK) return rc;

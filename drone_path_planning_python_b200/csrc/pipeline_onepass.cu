@@ -44,8 +44,32 @@
 namespace mst {
 
 constexpr int ONEPASS_MAX_WARPS = 11;
-constexpr int ONEPASS_TREGS = 4, ONEPASS_WREGS = 12;  // register tile of the input pipeline, doubles per lane
 
+// Guided schedule of the sampling phase: the CTA's trajectory slots [0, total) are cut into chunks
+// of 4, then 2, then 1 trajectories; warps draw chunk numbers from a shared-memory counter.  Long
+// chunks keep the lanes full (a warp's 32 consecutive samples run across the trajectories of its
+// chunk), single trajectories at the end keep the warps' finishing times within one trajectory.
+__device__ __forceinline__ void chunk_range(int k, int total, int& lo, int& hi) {
+  const int n4 = (total * 5 / 8) / 4, a = 4 * n4;
+  const int n2 = ((total - a) * 5 / 8) / 2, b = a + 2 * n2;
+  if (k < n4) { lo = 4 * k; hi = lo + 4; }
+  else if (k < n4 + n2) { lo = a + 2 * (k - n4); hi = lo + 2; }
+  else { lo = b + (k - n4 - n2); hi = lo + 1; }
+  if (hi > total) hi = total;
+}
+
+// The kernel runs in CTA-wide ROUNDS of three phases, one persistent CTA per SM:
+//   phase 1  every warp solves its own tile (32/(G*K) time groups) and builds the tile's tables;
+//   phase 2  the trajectories of all the CTA's tiles are sampled and collision-checked, handed out
+//            to the warps chunk by chunk (chunk_range) — any warp reads any tile's knot states;
+//   phase 3  every warp stores its tile's flag rows.
+// Why phases: the first version let every warp walk solve -> sample -> collide on its own.  Its hot
+// code (~5,000 instructions, 80 kB) then lived in the instruction cache (32 kB L1.5 per SM) all at
+// once, warps being in different places: 5.9 of every 10 issue-slot cycles waited for instructions
+// (profiles/r2_onepass_history.md) and the step took 8.0 ms.  With the warps of an SM in the same
+// phase the working set is the phase's code: ~20 kB (solve) or ~24 kB (sample + collide).
+// Poses still waiting in a warp's ring at the end of a round stay there: their flag bytes were stored
+// as 0 with the tile's rows and are overwritten in HBM when the pose turns out to collide.
 template <int K>
 __global__ void __launch_bounds__(32 * ONEPASS_MAX_WARPS, 1)
 onepass_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps, int groups, int n, int G, int S,
@@ -57,265 +81,326 @@ onepass_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps
   constexpr int NP = PoseDim<POSE>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
+  __shared__ int s_set0[2];                      // first set of this round / of the next one
+  __shared__ int s_chunk;                        // chunk counter of the sampling phase
+  __shared__ unsigned s_okl[ONEPASS_MAX_WARPS];  // per tile: bit g * R set when group g was solved here
+  // per trajectory slot of a round: tile | trajectory in the tile << 8 | group << 16 | drone << 24 (fixed for
+  // the launch: no integer divisions in the sampling loop), and whether the slot was solved in this round
+  __shared__ unsigned s_slot[ONEPASS_MAX_WARPS * 16];
+  __shared__ unsigned char s_ok[ONEPASS_MAX_WARPS * 16];
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   stage_meshes(smem_raw, robot_img, rl.bytes, env_img, el.bytes, &bar);
   const MeshView rb = mesh_view(smem_raw, rl);
   const MeshView ev = mesh_view(smem_raw + rl.bytes, el);
   double* nv = reinterpret_cast<double*>(smem_raw + rl.bytes + el.bytes);
   if (POSE == 0) build_plane_vertex_table(rb, ev, nv);
+  const int R = G * K, GPW = L.GPW, TPT = L.TPT;
+  const long long sets = ((long long)groups + GPW - 1) / GPW;
+  if (threadIdx.x == 0) s_set0[0] = atomicAdd(counters + 1, W);
+  for (int slot = threadIdx.x; slot < W * TPT; slot += blockDim.x) {
+    const int tw = slot / TPT, q = slot - tw * TPT, g = q / G;
+    s_slot[slot] = (unsigned)tw | ((unsigned)q << 8) | ((unsigned)g << 16) | ((unsigned)(q - g * G) << 24);
+  }
+  const unsigned magic_n = 0xffffffffu / (unsigned)n + 1u;   // item / n == __umulhi(item, magic_n) for the small items here
   __syncthreads();
 
-  const int R = G * K, GPW = L.GPW, TPT = L.TPT;
   const int gl = lane / R, col = lane - gl * R;
   const int d = col / K, k = col - d * K;
   const bool lane_used = gl < GPW;
-  unsigned char* wbase = smem_raw + L.shared_bytes + (size_t)warp * L.bytes;
+  unsigned char* const tiles = smem_raw + L.shared_bytes;          // tile w of the round lives at tiles + w * L.bytes
+  unsigned char* const wbase = tiles + (size_t)warp * L.bytes;
   double* wrho = reinterpret_cast<double*>(wbase + L.off_rho);    // [n][GPW]   1 / T
   double* wfac = reinterpret_cast<double*>(wbase + L.off_fac);    // [6(n-1)][GPW], later cbuf | dt | thr
   double* wy = reinterpret_cast<double*>(wbase + L.off_y);        // [3(n-1)][32] forward values, then knot states
   double* wt = reinterpret_cast<double*>(wbase + L.off_t);        // [GPW][n+1] stamps, later running duration sums
   double* ww = reinterpret_cast<double*>(wbase + L.off_w);        // [TPT][n+1][K] waypoints
-  double* cbuf = wfac;                                            // [2][n][K][8] staged coefficients
-  double* dts = wfac + L.cbuf_doubles;                            // [GPW]
-  int* thr = reinterpret_cast<int*>(dts + GPW);                   // [GPW][n]
-  uint8_t* hitb = wbase + L.off_hit;                              // [TPT][S] flags of the tile
-  uint8_t* anyb = wbase + L.off_any;                              // [TPT]
+  double* cbuf = wfac;                                            // [2][n][K][8] coefficients staged by THIS warp
+  const size_t off_dts = L.off_fac + sizeof(double) * L.cbuf_doubles;   // [GPW] sample spacing, then [GPW][n] thresholds
+  double* dts = reinterpret_cast<double*>(wbase + off_dts);
+  int* thr = reinterpret_cast<int*>(dts + GPW);
   uint8_t* piece_of = wbase + L.off_piece;                        // [GPW][S]
   double* wT = reinterpret_cast<double*>(wbase + L.off_wire);     // wire mode: [GPW][n] durations T_i, then
   float* wstage = reinterpret_cast<float*>(wT + (size_t)GPW * n); //   [n][1 + 8K] one trajectory's float32 matrix
   PoseRing<NP>& ring = *reinterpret_cast<PoseRing<NP>*>(wbase + L.off_ring);
   unsigned ring_head = 0u, ring_tail = 0u;  // warp-uniform
   const bool wire_mat = wire.count > 0 && wire.mat[0] != nullptr;
+  const int width = 1 + MST_NCOEF * K;
 
-  auto report = [&](int q, int s, bool h) {
-    hitb[q * S + s] = h ? 1 : 0;
-    if (h) anyb[q] = 1;
+  int round = 0;                 // low 15 bits travel with every queued pose
+  long long round_b0 = 0;        // first trajectory of the CTA's current round
+  bool sampling = false;         // true while this round's flag rows are still in shared memory
+  // a decided pose: only collisions need recording (its flag byte was preset to 0)
+  auto report = [&](int b, int id1, bool h) {
+    if (!h) return;
+    const int s = id1 & 0xffff;
+    if (sampling && ((id1 >> 16) & 0x7fff) == (round & 0x7fff)) {
+      const unsigned si = s_slot[(int)(b - round_b0)];
+      unsigned char* tb = tiles + (size_t)(si & 0xff) * L.bytes;
+      const int q = (si >> 8) & 0xff;
+      tb[L.off_hit + (size_t)q * S + s] = 1;
+      tb[L.off_any + q] = 1;
+    } else {  // a pose of an earlier round: its rows are in HBM already
+      hit[(size_t)b * S + s] = 1;
+      any_hit[b] = 1;
+      for (int t = 0; t < wire.count; ++t)
+        if (wire.hit[t] != nullptr) {
+          wire.hit[t][(size_t)(wire.row0 + b) * S + s] = 1;
+          wire.any[t][wire.row0 + b] = 1;
+        }
+    }
   };
 
-  const long long sets = ((long long)groups + GPW - 1) / GPW;
-  // sets are handed out by a ticket counter: a warp that meets the obstacle takes several times
-  // longer over a tile than one in free space, and a static stride left the last warps running alone
-  auto ticket = [&]() -> long long {
-    int tk = 0;
-    if (lane == 0) tk = atomicAdd(counters + 1, 1);
-    return (long long)__shfl_sync(FULL, tk, 0);
-  };
-  // software pipeline of the input copies (as in condensed_cols_kernel): the NEXT set's stamps and
-  // waypoints are loaded into registers before this set is worked on
-  const bool piped = GPW * (n + 1) <= 32 * ONEPASS_TREGS && GPW * (n + 1) * R <= 32 * ONEPASS_WREGS;
-  double tr[ONEPASS_TREGS], wr[ONEPASS_WREGS];
-  auto load_set = [&](long long set2) {
-    if (set2 >= sets) return;
-    const long long h0 = set2 * GPW;
-    const int c2 = (int)min((long long)GPW, groups - h0);
-    const double* tb = tstamps + (size_t)h0 * (n + 1);
-    const double* wb = wp + (size_t)h0 * (n + 1) * R;
-#pragma unroll
-    for (int j = 0; j < ONEPASS_TREGS; ++j) if (lane + 32 * j < c2 * (n + 1)) tr[j] = __ldg(tb + lane + 32 * j);
-#pragma unroll
-    for (int j = 0; j < ONEPASS_WREGS; ++j) if (lane + 32 * j < c2 * (n + 1) * R) wr[j] = __ldg(wb + lane + 32 * j);
-  };
-
-  long long set = ticket();
-  if (piped) load_set(set);
-  while (set < sets) {
-    const long long next_set = ticket();
+  int par = 0;
+  for (;;) {
+    const long long set0 = s_set0[par];
+    // epilogue round (no sets left): phases 1 and 3 are skipped, phase 2 only decides the poses still
+    // queued — through the SAME call site of the collision engine (one copy of its code in the kernel)
+    const bool last = set0 >= sets;
+    // ================= phase 1: this warp's tile =====================================================
+    if (threadIdx.x == 0 && !last) { s_set0[par ^ 1] = atomicAdd(counters + 1, W); s_chunk = 0; }
+    const long long set = set0 + warp;
     const long long g0 = set * GPW;
-    const int cnt = (int)min((long long)GPW, groups - g0);
+    const int cnt = last ? 0 : (int)max(0ll, min((long long)GPW, groups - g0));
     const int nbt = cnt * G;                 // trajectories of this tile
     const long long b0 = g0 * G;             // first trajectory of the tile
-    __syncwarp();
-    if (piped) {
-#pragma unroll
-      for (int j = 0; j < ONEPASS_TREGS; ++j) if (lane + 32 * j < cnt * (n + 1)) wt[lane + 32 * j] = tr[j];
-#pragma unroll
-      for (int j = 0; j < ONEPASS_WREGS; ++j) if (lane + 32 * j < cnt * (n + 1) * R) ww[lane + 32 * j] = wr[j];
-    } else {
-      for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = tstamps[(size_t)g0 * (n + 1) + i];
-      for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[i] = wp[(size_t)g0 * (n + 1) * R + i];
-    }
-    __syncwarp();
-    if (piped) load_set(next_set);
-
-    // ---- 1. solve: classification and factorisation by the group's first column ----------------
-    const bool mine = lane_used && gl < cnt;
-    const double* tg = wt + (size_t)gl * (n + 1);
-    int cls = 1;
-    if (mine && col == 0) {
-      double Tmin, Tmax;
-      cls = classify_times(tg, n, &Tmin, &Tmax);
-      if (cls != 0) {
-        list[atomicAdd(counters, 1)] = (int)(g0 + gl);   // pivoted solver + list-mode sampling finish it
-      } else {
-        double* rho = wrho + gl;
-        for (int i = 0; i < n; ++i) rho[(size_t)i * GPW] = tg[i + 1] - tg[i];
-        condensed_factor(n, rho, wfac + gl, GPW);
-      }
-    }
-    cls = __shfl_sync(FULL, cls, lane_used ? gl * R : 0);
-    const unsigned okl = __ballot_sync(FULL, mine && col == 0 && cls == 0);  // bit gl * R per solvable group
-    __syncwarp();
-    if (mine && cls == 0) {
-      const double* wcol = ww + ((size_t)gl * G + d) * (n + 1) * K + k;
-      condensed_forward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
-      condensed_backward_states<1>(n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
-    }
-    __syncwarp();
-    if (okl == 0u) { set = next_set; continue; }
-    auto group_ok = [&](int g) -> bool { return (okl >> (g * R)) & 1u; };
-
-    // ---- 2. per-tile tables ----------------------------------------------------------------------
-    // durations and status out (every trajectory of a group carries its own copy of the durations)
-    for (int item = lane; item < nbt * n; item += 32) {
-      const int q = item / n, i = item - q * n, g = q / G;
-      if (group_ok(g)) {
-        const double Ti = wt[g * (n + 1) + i + 1] - wt[g * (n + 1) + i];
-        dur[(size_t)(b0 + q) * n + i] = Ti;
-        if (wire_mat && q == g * G) wT[g * n + i] = Ti;
-      }
-    }
-    if (lane < nbt) {
-      anyb[lane] = 0;
-      if (group_ok(lane / G)) info[b0 + lane] = MST_INFO_OK;
-    }
-    __syncwarp();
-    // running sums of the durations in place of the stamps (left-to-right, as
-    // PiecewisePolynomial.eval accumulates t_counting) and the sample spacing
-    if (lane < cnt && group_ok(lane)) {
-      double* kn = wt + lane * (n + 1);
-      double prev = kn[0], acc = 0.0;
-      kn[0] = 0.0;
-#pragma unroll 1
-      for (int i = 0; i < n; ++i) {
-        const double nx = kn[i + 1];
-        acc = __dadd_rn(acc, nx - prev);
-        prev = nx;
-        kn[i + 1] = acc;
-      }
-      dts[lane] = __ddiv_rn(acc, (double)S);
-    }
-    __syncwarp();
-    // thresholds: first s with !(s * dt < knot), found from the quotient and corrected with the very
-    // comparison PiecewisePolynomial.eval makes (t is non-decreasing in s)
-#pragma unroll 1
-    for (int item = lane; item < cnt * n; item += 32) {
-      const int g = item / n, i = item - g * n;
-      int first = S;
-      if (i < n - 1 && group_ok(g)) {
-        const double knot = wt[g * (n + 1) + i + 1], dt = dts[g];
-        first = (int)fmin(fmax(ceil(__ddiv_rn(knot, dt)), 0.0), (double)S);
-        while (first > 0 && !(__dmul_rn((double)(first - 1), dt) < knot)) --first;
-        while (first < S && __dmul_rn((double)first, dt) < knot) ++first;
-      }
-      thr[item] = first;  // thr[g][n-1] = S closes the last piece
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int item = lane; item < cnt * n; item += 32) {
-      const int g = item / n, i = item - g * n;
-      if (group_ok(g)) {
-        const int from = i ? thr[item - 1] : 0, to = thr[item];
-#pragma unroll 1
-        for (int x = from; x < to; ++x) piece_of[g * S + x] = (uint8_t)i;
-      }
-    }
-    __syncwarp();
-
-    // ---- 3. coefficients of trajectory q: formed once, stored once, staged for its samples -----------
-    auto stage_trajectory = [&](int q) {
-      const int g = q / G;
-      if (!group_ok(g)) return;
-      double* cb = cbuf + (size_t)(q & 1) * n * K * MST_NCOEF;
-      double* cd = coef + (size_t)(b0 + q) * n * K * MST_NCOEF;
-#pragma unroll 1
-      for (int item = lane; item < n * K; item += 32) {
-        const int i = item / K, kk = item - i * K;
-        const int c = q * K + kk;   // the lane that solved this column
-        double v0 = 0.0, a0 = 0.0, j0 = 0.0, v1 = 0.0, a1 = 0.0, j1 = 0.0;
-        if (i >= 1) { const double* x = wy + (size_t)(i - 1) * 3 * 32 + c; v0 = x[0]; a0 = x[32]; j0 = x[64]; }
-        if (i + 1 < n) { const double* x = wy + (size_t)i * 3 * 32 + c; v1 = x[0]; a1 = x[32]; j1 = x[64]; }
-        const double w0 = ww[((size_t)q * (n + 1) + i) * K + kk], w1 = ww[((size_t)q * (n + 1) + i + 1) * K + kk];
-        double cc[MST_NCOEF];
-        piece_coefficients(w0, w1 - w0, v0, a0, j0, v1, a1, j1, wrho[(size_t)i * GPW + g], cc);
-        double2* s2 = reinterpret_cast<double2*>(cb + (size_t)item * MST_NCOEF);
-        double2* g2 = reinterpret_cast<double2*>(cd + (size_t)item * MST_NCOEF);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double2 v = make_double2(cc[2 * e], cc[2 * e + 1]);
-          s2[e] = v;
-          g2[e] = v;
-        }
-        if (wire_mat) {
-          float* ws = wstage + i * (1 + MST_NCOEF * K) + 1 + MST_NCOEF * kk;
-#pragma unroll
-          for (int e = 0; e < MST_NCOEF; ++e) ws[e] = (float)cc[e];
-          if (kk == 0) wstage[i * (1 + MST_NCOEF * K)] = (float)wT[g * n + i];
+    round_b0 = set0 * GPW * G;
+    unsigned okl = 0u;
+    if (cnt > 0) {
+      for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = __ldg(tstamps + (size_t)g0 * (n + 1) + i);
+      for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[i] = __ldg(wp + (size_t)g0 * (n + 1) * R + i);
+      __syncwarp();
+      const bool mine = lane_used && gl < cnt;
+      const double* tg = wt + (size_t)gl * (n + 1);
+      int cls = 1;
+      if (mine && col == 0) {
+        double Tmin, Tmax;
+        cls = classify_times(tg, n, &Tmin, &Tmax);
+        if (cls != 0) {
+          list[atomicAdd(counters, 1)] = (int)(g0 + gl);   // pivoted solver + list-mode sampling finish it
+        } else {
+          double* rho = wrho + gl;
+          for (int i = 0; i < n; ++i) rho[(size_t)i * GPW] = tg[i + 1] - tg[i];
+          condensed_factor(n, rho, wfac + gl, GPW);
         }
       }
-      if (wire_mat) {
-        __syncwarp();
-        const int words = n * (1 + MST_NCOEF * K);
-        const size_t row = (size_t)(wire.row0 + b0 + q) * words;
-        for (int t = 0; t < wire.count; ++t) {
-          float* dst = wire.mat[t] + row;
-          if (wire.mat[t] != nullptr)
-            for (int w = lane; w < words; w += 32) dst[w] = wstage[w];
+      cls = __shfl_sync(FULL, cls, lane_used ? gl * R : 0);
+      okl = __ballot_sync(FULL, mine && col == 0 && cls == 0);  // bit gl * R per solvable group
+      __syncwarp();
+      if (mine && cls == 0) {
+        const double* wcol = ww + ((size_t)gl * G + d) * (n + 1) * K + k;
+        condensed_forward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
+        condensed_backward_states<1>(n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) s_okl[warp] = okl;
+    if (lane < TPT) s_ok[warp * TPT + lane] = (lane < nbt && ((okl >> ((lane / G) * R)) & 1u)) ? 1 : 0;
+    if (okl != 0u) {
+      auto group_ok = [&](int g) -> bool { return (okl >> (g * R)) & 1u; };
+      // durations and status out (every trajectory of a group carries its own copy of the durations)
+      for (int item = lane; item < nbt * n; item += 32) {
+        const int q = (int)__umulhi((unsigned)item, magic_n), i = item - q * n, g = (int)((s_slot[q] >> 16) & 0xffu);
+        if (group_ok(g)) {
+          const double Ti = wt[g * (n + 1) + i + 1] - wt[g * (n + 1) + i];
+          dur[(size_t)(b0 + q) * n + i] = Ti;
+          if (wire_mat && q == g * G) wT[g * n + i] = Ti;
         }
       }
-    };
-
-    // ---- 4. sampling and collision -------------------------------------------------------------------
-    const int work = nbt * S;
-    int tl = 0, s = lane, dd = 0, gq = 0;   // (trajectory, sample) of this lane; drone and group of tl
-    int next_stage = 0;
-    for (int base = 0; base < work; base += 32, s += 32) {
-      // trajectory q is staged when the sampling front has left trajectory q - 2 (whose buffer it takes)
-      while (next_stage < nbt && (next_stage < 2 || base >= (next_stage - 1) * S)) {
-        __syncwarp();
-        stage_trajectory(next_stage);
-        ++next_stage;
-        __syncwarp();
+      if (lane < nbt) {
+        wbase[L.off_any + lane] = 0;
+        if (group_ok(lane / G)) info[b0 + lane] = MST_INFO_OK;
       }
-      while (s >= S) { s -= S; ++tl; if (++dd == G) { dd = 0; ++gq; } }
-      const int idx = base + lane;
-      bool active = idx < work;
-      if (!active) { tl = nbt - 1; s = S - 1; gq = (nbt - 1) / G; }   // parked on the tile's last sample (not reported)
-      active = active && group_ok(gq);
-      const double t = __dmul_rn((double)s, dts[gq]);
-      const int piece = min((int)piece_of[gq * S + s], n - 1);
-      const double local = __dsub_rn(t, wt[gq * (n + 1) + piece]);
-      const double* cp = cbuf + (((size_t)(tl & 1) * n + piece) * K) * MST_NCOEF;
-      double pos[K];
-#pragma unroll
-      for (int a = 0; a < K; ++a) {
-        const double2* src = reinterpret_cast<const double2*>(cp + a * MST_NCOEF);
-        const double2 c01 = src[0], c23 = src[1], c45 = src[2], c67 = src[3];
-        double x = c67.y;  // 0*t + c7
-        x = __dadd_rn(__dmul_rn(x, local), c67.x);
-        x = __dadd_rn(__dmul_rn(x, local), c45.y);
-        x = __dadd_rn(__dmul_rn(x, local), c45.x);
-        x = __dadd_rn(__dmul_rn(x, local), c23.y);
-        x = __dadd_rn(__dmul_rn(x, local), c23.x);
-        x = __dadd_rn(__dmul_rn(x, local), c01.y);
-        x = __dadd_rn(__dmul_rn(x, local), c01.x);
-        pos[a] = x;
+      __syncwarp();
+      // running sums of the durations in place of the stamps (left-to-right, as
+      // PiecewisePolynomial.eval accumulates t_counting) and the sample spacing
+      if (lane < cnt && group_ok(lane)) {
+        double* kn = wt + lane * (n + 1);
+        double prev = kn[0], acc = 0.0;
+        kn[0] = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+          const double nx = kn[i + 1];
+          acc = __dadd_rn(acc, nx - prev);
+          prev = nx;
+          kn[i + 1] = acc;
+        }
+        dts[lane] = __ddiv_rn(acc, (double)S);
       }
-      double pp[NP];
-      pp[0] = pos[0]; pp[1] = pos[1]; pp[2] = pos[2];
-      if (POSE == 1) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
-      const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
-      if (active && !near) hitb[tl * S + s] = 0;
-      ring_push<POSE>(ring, ring_tail, near, pp, tl, s, -1, 0u, 0u);
-      while (ring_tail - ring_head >= 32u) ring_drain<POSE>(ring, ring_head, ring_tail, 32, rb, rbb, ev, nv, report);
+      __syncwarp();
+      // thresholds: first s with !(s * dt < knot), found from the quotient and corrected with the very
+      // comparison PiecewisePolynomial.eval makes (t is non-decreasing in s)
+#pragma unroll 1
+      for (int item = lane; item < cnt * n; item += 32) {
+        const int g = (int)__umulhi((unsigned)item, magic_n), i = item - g * n;
+        int first = S;
+        if (i < n - 1 && group_ok(g)) {
+          const double knot = wt[g * (n + 1) + i + 1], dt = dts[g];
+          first = (int)fmin(fmax(ceil(__ddiv_rn(knot, dt)), 0.0), (double)S);
+          while (first > 0 && !(__dmul_rn((double)(first - 1), dt) < knot)) --first;
+          while (first < S && __dmul_rn((double)first, dt) < knot) ++first;
+        }
+        thr[item] = first;  // thr[g][n-1] = S closes the last piece
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int item = lane; item < cnt * n; item += 32) {
+        const int g = (int)__umulhi((unsigned)item, magic_n), i = item - g * n;
+        if (group_ok(g)) {
+          const int from = i ? thr[item - 1] : 0, to = thr[item];
+#pragma unroll 1
+          for (int x = from; x < to; ++x) piece_of[g * S + x] = (uint8_t)i;
+        }
+      }
     }
-    // the tile's flags leave as whole rows: every queued pose is decided first
-    while (ring_tail != ring_head)
-      ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
-    __syncwarp();
-    {
-      const int targets = wire.count > 0 ? wire.count : 0;
-      for (int t = -1; t < targets; ++t) {
+    sampling = !last;
+    // all tiles of the round are solved; s_set0[par ^ 1], s_chunk, s_okl are visible.  (Epilogue: every
+    // warp has stored its last rows — a row store must not land on top of a late flag.)
+    __syncthreads();
+
+    // ================= phase 2: sample + collide, trajectories handed out chunk by chunk =============
+    if (!last) {
+      // next round's inputs towards L2 while this round's samples are worked on
+      const long long nset = (long long)s_set0[par ^ 1] + warp;
+      if (nset < sets) {
+        const long long h0 = nset * GPW;
+        const int c2 = (int)min((long long)GPW, groups - h0);
+        const char* tb = reinterpret_cast<const char*>(tstamps + (size_t)h0 * (n + 1));
+        const char* wb = reinterpret_cast<const char*>(wp + (size_t)h0 * (n + 1) * R);
+        for (int off = lane * 128; off < c2 * (n + 1) * 8; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + off));
+        for (int off = lane * 128; off < c2 * (n + 1) * R * 8; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wb + off));
+      }
+    }
+    const int total = W * TPT;
+    for (;;) {
+      int lo = total, hi = total;
+      if (!last) {
+        int ck = 0;
+        if (lane == 0) ck = atomicAdd(&s_chunk, 1);
+        ck = __shfl_sync(FULL, ck, 0);
+        chunk_range(ck, total, lo, hi);
+        if (lo >= total) break;
+      }
+      const int nb = hi - lo, work = nb * S;
+      // slot -> tile, trajectory within the tile, group, drone; advanced incrementally with tl
+      int tw = 0, q = 0, g = 0, dd = 0;
+      if (lo < total) { const unsigned si = s_slot[lo]; tw = si & 0xff; q = (si >> 8) & 0xff; g = (si >> 16) & 0xff; dd = si >> 24; }
+      int tl = 0, s = lane, next_stage = 0;
+      for (int base = 0;; base += 32, s += 32) {
+        const bool more = base < work;
+        if (more) {
+        // trajectory j of the chunk is staged when the sampling front has left trajectory j - 2
+        while (next_stage < nb && (next_stage < 2 || base >= (next_stage - 1) * S)) {
+          __syncwarp();
+          const int slot = lo + next_stage;
+          const unsigned ssi = s_slot[slot];
+          const int stw = ssi & 0xff, sq = (ssi >> 8) & 0xff, sg = (ssi >> 16) & 0xff;
+          unsigned char* tb = tiles + (size_t)stw * L.bytes;
+          if (s_ok[slot]) {
+            const double* xy = reinterpret_cast<const double*>(tb + L.off_y);
+            const double* xw = reinterpret_cast<const double*>(tb + L.off_w);
+            const double* xrho = reinterpret_cast<const double*>(tb + L.off_rho);
+            const double* xT = reinterpret_cast<const double*>(tb + L.off_wire);
+            const long long bq = (round_b0 + slot);
+            double* cb = cbuf + (size_t)(next_stage & 1) * n * K * MST_NCOEF;
+            double* cd = coef + (size_t)bq * n * K * MST_NCOEF;
+#pragma unroll 1
+            for (int item = lane; item < n * K; item += 32) {
+              const int i = item / K, kk = item - i * K;
+              const int c = sq * K + kk;   // the lane that solved this column
+              double v0 = 0.0, a0 = 0.0, j0 = 0.0, v1 = 0.0, a1 = 0.0, j1 = 0.0;
+              if (i >= 1) { const double* x = xy + (size_t)(i - 1) * 3 * 32 + c; v0 = x[0]; a0 = x[32]; j0 = x[64]; }
+              if (i + 1 < n) { const double* x = xy + (size_t)i * 3 * 32 + c; v1 = x[0]; a1 = x[32]; j1 = x[64]; }
+              const double w0 = xw[((size_t)sq * (n + 1) + i) * K + kk], w1 = xw[((size_t)sq * (n + 1) + i + 1) * K + kk];
+              double cc[MST_NCOEF];
+              piece_coefficients(w0, w1 - w0, v0, a0, j0, v1, a1, j1, xrho[(size_t)i * GPW + sg], cc);
+              double2* s2 = reinterpret_cast<double2*>(cb + (size_t)item * MST_NCOEF);
+              double2* g2 = reinterpret_cast<double2*>(cd + (size_t)item * MST_NCOEF);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const double2 v = make_double2(cc[2 * e], cc[2 * e + 1]);
+                s2[e] = v;
+                g2[e] = v;
+              }
+              if (wire_mat) {
+                float* ws = wstage + i * width + 1 + MST_NCOEF * kk;
+#pragma unroll
+                for (int e = 0; e < MST_NCOEF; ++e) ws[e] = (float)cc[e];
+                if (kk == 0) wstage[i * width] = (float)xT[sg * n + i];
+              }
+            }
+            if (wire_mat) {
+              __syncwarp();
+              const int words = n * width;
+              const size_t row = (size_t)(wire.row0 + bq) * words;
+              for (int t = 0; t < wire.count; ++t)
+                if (wire.mat[t] != nullptr) {
+                  float* dst = wire.mat[t] + row;
+                  for (int w = lane; w < words; w += 32) dst[w] = wstage[w];
+                }
+            }
+          }
+          ++next_stage;
+          __syncwarp();
+        }
+        while (s >= S) {
+          s -= S; ++tl; ++q;
+          if (++dd == G) { dd = 0; ++g; }
+          if (q == TPT) { q = 0; g = 0; dd = 0; ++tw; }
+        }
+        bool active = base + lane < work;
+        if (!active) {   // parked on the chunk's last sample (not recorded)
+          const unsigned si = s_slot[hi - 1];
+          tl = nb - 1; s = S - 1; tw = si & 0xff; q = (si >> 8) & 0xff; g = (si >> 16) & 0xff; dd = si >> 24;
+        }
+        const unsigned char* tb = tiles + (size_t)tw * L.bytes;
+        active = active && s_ok[lo + tl];
+        const double* kn = reinterpret_cast<const double*>(tb + L.off_t) + g * (n + 1);
+        const double t = __dmul_rn((double)s, reinterpret_cast<const double*>(tb + off_dts)[g]);
+        const int piece = min((int)tb[L.off_piece + (size_t)g * S + s], n - 1);
+        const double local = __dsub_rn(t, kn[piece]);
+        const double* cp = cbuf + (((size_t)(tl & 1) * n + piece) * K) * MST_NCOEF;
+        double pos[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          const double2* src = reinterpret_cast<const double2*>(cp + a * MST_NCOEF);
+          const double2 c01 = src[0], c23 = src[1], c45 = src[2], c67 = src[3];
+          double x = c67.y;  // 0*t + c7
+          x = __dadd_rn(__dmul_rn(x, local), c67.x);
+          x = __dadd_rn(__dmul_rn(x, local), c45.y);
+          x = __dadd_rn(__dmul_rn(x, local), c45.x);
+          x = __dadd_rn(__dmul_rn(x, local), c23.y);
+          x = __dadd_rn(__dmul_rn(x, local), c23.x);
+          x = __dadd_rn(__dmul_rn(x, local), c01.y);
+          x = __dadd_rn(__dmul_rn(x, local), c01.x);
+          pos[a] = x;
+        }
+        double pp[NP];
+        pp[0] = pos[0]; pp[1] = pos[1]; pp[2] = pos[2];
+        if (POSE == 1) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
+        const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
+        // every flag starts as 0; a queued pose that turns out to collide overwrites its byte
+        if (active) const_cast<unsigned char*>(tb)[L.off_hit + (size_t)q * S + s] = 0;
+        ring_push<POSE>(ring, ring_tail, near, pp, (int)(round_b0 + lo + tl), s | ((round & 0x7fff) << 16), -1, 0u, 0u);
+        }
+        // full batches of 32 while sampling; in the epilogue whatever is left
+        const unsigned enough = (more || !last) ? 32u : 1u;
+        while (ring_tail - ring_head >= enough)
+          ring_drain<POSE>(ring, ring_head, ring_tail, (int)min(32u, ring_tail - ring_head), rb, rbb, ev, nv, report);
+        if (!more) break;
+      }
+      if (last) break;
+    }
+    if (last) break;
+    __syncthreads();   // every sample of the round is recorded (poses still queued: byte 0 for now)
+    sampling = false;
+
+    // ================= phase 3: this tile's flag rows =================================================
+    if (okl != 0u) {
+      auto group_ok = [&](int g) -> bool { return (okl >> (g * R)) & 1u; };
+      const uint8_t* hitb = wbase + L.off_hit;
+      const uint8_t* anyb = wbase + L.off_any;
+      for (int t = -1; t < wire.count; ++t) {
         uint8_t* hdst = t < 0 ? hit : wire.hit[t];
         uint8_t* adst = t < 0 ? any_hit : wire.any[t];
         const size_t off = (size_t)(t < 0 ? 0 : wire.row0) + (size_t)b0;
@@ -324,8 +409,12 @@ onepass_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps
           const unsigned* src = reinterpret_cast<const unsigned*>(hitb);
           unsigned* dst = reinterpret_cast<unsigned*>(hdst + off * S);
           const int wpr = S >> 2;   // words per row
-          for (int w = lane; w < nbt * wpr; w += 32)
-            if (group_ok((w / wpr) / G)) dst[w] = src[w];
+          if (__popc(okl) == cnt) {   // the usual case: every group of the tile was solved here
+            for (int w = lane; w < nbt * wpr; w += 32) dst[w] = src[w];
+          } else {
+            for (int w = lane; w < nbt * wpr; w += 32)
+              if (group_ok((w / wpr) / G)) dst[w] = src[w];
+          }
         } else {
           for (int w = lane; w < nbt * S; w += 32)
             if (group_ok((w / S) / G)) hdst[off * S + w] = hitb[w];
@@ -333,8 +422,13 @@ onepass_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps
         if (lane < nbt && group_ok(lane / G)) adst[off + lane] = anyb[lane];
       }
     }
-    set = next_set;
+    ++round;
+    par ^= 1;
+    // the next round's phase 1 only touches this warp's own solver arrays and tables; the flag rows
+    // are not written again before the next phase-1 barrier
   }
+  // A queued pose is at most a few hundred rounds old (the pipeline cuts batches into chunks of 2^22
+  // trajectories), far from the 2^15 rounds its round tag can tell apart.
 }
 
 // Wire outputs of the time groups the single-pass kernel handed to the pivoted solver: packed /

@@ -65,7 +65,14 @@ enum {
                             groups it cannot take (t[0] != 0, zero-length piece) are
                             reported through info[]                                        */
   MST_SOLVER_BANDED_LU = 1,
-  MST_SOLVER_CONDENSED = 2
+  MST_SOLVER_CONDENSED = 2,
+  MST_SOLVER_AUTO_ONE_PASS = 3 /* mst_pipeline only: MST_SOLVER_AUTO's solver choice, run by the
+                                  single-pass kernel (solve + sample + collide in one persistent
+                                  launch; the coefficients reach HBM once and are never read back)
+                                  when the sizes suit it: K = 3 / 4, 2 <= n <= 32, 32 <= S <= 4096,
+                                  G*K <= 32.  Identical results; on B200 the two-launch pipeline
+                                  is the faster one, so MST_SOLVER_AUTO runs that
+                                  (MST_PIPELINE_ONE_PASS=1 in the environment switches it)          */
 };
 
 /* piece selection semantics for mst_sample_batch */
@@ -245,9 +252,8 @@ int mst_collide_trajectories(const double* coef, const double* dur, int B, int n
 /*
  * Fused pipeline: solve -> sample S uniform times -> place the robot mesh at every
  * sampled position (yaw = sampled 4th axis when K = 4, else 0) -> collide.
- * One persistent kernel (the coefficients reach HBM once and are never read back) when the sizes
- * suit it (K = 3 / 4, 2 <= n <= 32, 32 <= S <= 4096, G*K <= 32, MST_SOLVER_AUTO); the two-launch
- * pipeline (solver, then sample + collide) otherwise.  Results are identical either way.
+ * Two launches (solver, then sample + collide) or, with MST_SOLVER_AUTO_ONE_PASS, one persistent
+ * kernel (see the solver enum).  Results are identical either way.
  *   inputs / coef / dur / info as mst_solve_batch
  *   hit     [B][S]  per-sample collision flag
  *   any_hit [B]     1 iff any sample of the trajectory collides

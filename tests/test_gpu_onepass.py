@@ -66,7 +66,7 @@ def test_single_pass_equals_separate_stages(K, G, n, S, B):
     rng = np.random.default_rng(1000 * K + 10 * G + n)
     robot, env = _meshes()
     wp, t = _workload(rng, B, n, K, G)
-    res = mst.pipeline(wp, t, S, robot, env, share_time_group=G)
+    res = mst.pipeline(wp, t, S, robot, env, share_time_group=G, solver="auto_one_pass")
     coef, dur, info, hit, any_hit = _separate(mst, wp, t, S, robot, env, G)
     assert int((info != 0).sum()) == 0
     assert _same(res.coef, coef) and _same(res.dur, dur) and torch.equal(res.info, info)
@@ -91,7 +91,7 @@ def test_single_pass_with_groups_for_the_pivoted_solver(K, G):
                              torch.full((B,), 99, dtype=torch.int32, device="cuda"),
                              torch.full((B, S), 9, dtype=torch.uint8, device="cuda"),
                              torch.full((B,), 9, dtype=torch.uint8, device="cuda"))
-    res = mst.pipeline(wp, t, S, robot, env, share_time_group=G, out=out)
+    res = mst.pipeline(wp, t, S, robot, env, share_time_group=G, out=out, solver="auto_one_pass")
     coef, dur, info, hit, any_hit = _separate(mst, wp, t, S, robot, env, G)
     assert torch.equal(res.info, info)
     codes = info.view(-1, G)[:, 0].cpu().numpy()
@@ -114,7 +114,7 @@ def test_single_pass_vs_oracle():
     for K in (3, 4):
         B, n, S = 512, 10, 100
         wp, t = _workload(rng, B, n, K)
-        res = mst.pipeline(wp, t, S, robot, env)
+        res = mst.pipeline(wp, t, S, robot, env, solver="auto_one_pass")
         ref_coef, ref_pos, ref_hit = oracle_pipeline(wp, t, S, robot_tris, env_tris)
         got = res.coef.cpu().numpy()
         err = np.abs(got - ref_coef).max(axis=(1, 3)) / np.abs(ref_coef).max(axis=(1, 3))

@@ -4,9 +4,9 @@
   ncu -i X.ncu-rep --page source --print-source cuda,sass --csv > src.csv
   python tools/ncu_summary.py counters raw.csv            > profiles/..._ncu.txt
   python tools/ncu_summary.py lines src.csv KERNEL [N]    > profiles/..._hot_lines.txt
-  python tools/ncu_summary.py json raw.csv KERNEL TRAJECTORIES > profiles/r2_onepass_counters.json
-      (per-trajectory DRAM bytes and executed FP64 instructions of KERNEL: what bench.py reads for
-       roofline.traffic and the FP64 fraction)
+  python tools/ncu_summary.py json raw.csv TRAJECTORIES KERNEL [KERNEL ...] > profiles/r2_kernel_counters.json
+      (per-trajectory DRAM bytes and executed FP64 instructions of each KERNEL, first matching launch:
+       what bench.py reads for roofline.traffic and the FP64 fraction)
 """
 import csv, sys, collections
 
@@ -46,8 +46,15 @@ def _num(x):
         return None
 
 
-def as_json(path, kernel, trajectories):
+def as_json(path, trajectories, kernels):
     import json
+    out = {}
+    for kernel in kernels:
+        out[kernel] = one_kernel(path, kernel, trajectories)
+    print(json.dumps(out, indent=1))
+
+
+def one_kernel(path, kernel, trajectories):
     rows = list(csv.reader(open(path)))
     head, units = rows[0], rows[1]
     for row in rows[2:]:
@@ -82,8 +89,7 @@ def as_json(path, kernel, trajectories):
         if None not in (dfma, dmul, dadd):
             out["fp64_instructions_per_trajectory"] = (dfma + dmul + dadd) / trajectories
             out["fp64_flops_per_trajectory"] = (2 * dfma + dmul + dadd) / trajectories
-        print(json.dumps(out, indent=1))
-        return
+        return out
     raise SystemExit("kernel %s not in %s" % (kernel, path))
 
 
@@ -133,6 +139,6 @@ if __name__ == "__main__":
     if sys.argv[1] == "counters":
         counters(sys.argv[2])
     elif sys.argv[1] == "json":
-        as_json(sys.argv[2], sys.argv[3], int(sys.argv[4]))
+        as_json(sys.argv[2], int(sys.argv[3]), sys.argv[4:])
     else:
         lines(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40)
