@@ -310,40 +310,57 @@ def run_ours(args):
         return float(ms.item())
 
     # ---- multi-GPU data planes: what is gathered, and how -------------------------------
-    # default "f32-wire": the float32 polynomial matrix the reference's path_to_pol emits + the flags,
-    # stored to every peer's buffer from INSIDE the single-pass kernel (NVLink peer stores);
-    # "flags-only": flags alone, same mechanism; "f64-full": FP64 coefficients + flags pushed by the
-    # copy engines chunk by chunk (round 1's data plane).
+    # WHAT: "f32-wire" = what the reference produces, path_to_pol's float32 polynomial matrix + the flags
+    # (default); "flags-only"; "f64-full" = FP64 coefficients + flags (round 1's figure).
+    # HOW: "push" = the two-launch pipeline writes into this rank's slot of a symmetric buffer and the copy
+    # engines push the slot into every peer's buffer chunk by chunk; "store" = the single-pass kernel
+    # stores every finished trajectory through all peer pointers itself (mst_pipeline_wire).
     from drone_path_planning_python_b200.distributed import PeerPushAllGather, PeerStoreGather
-    gathers, gather_note = {}, None
+    modes = {}
     if world > 1:
-        gathers["f32-wire"] = PeerStoreGather(B, world, rank, N_SEG, K_AX, S_SAMPLES, dev, mode="pol_matrix_f32")
-        gathers["flags-only"] = PeerStoreGather(B, world, rank, N_SEG, K_AX, S_SAMPLES, dev, mode="flags")
         if args.gather_chunks <= 0:
             args.gather_chunks = 4 if world <= 4 else 2
-        gathers["f64-full"] = PeerPushAllGather(B, world, rank, args.gather_chunks, [res.coef, res.hit, res.any_hit],
-                                                streams=args.push_streams)
-        gather_note = ("%s: in-kernel NVLink peer stores of path_to_pol's float32 matrix + flags (mst_pipeline_wire, "
-                       "symmetric memory)" % args.gather)
+        mat_t = torch.empty((1, N_SEG, 1 + 8 * K_AX), dtype=torch.float32, device=dev)
 
-    push = gathers.get("f64-full")
-    push_res = None if push is None else mst.PipelineResult(push.local_slot(0), res.dur, res.info, push.local_slot(1),
-                                                            push.local_slot(2))
+        def push_mode(what):
+            tmpl = {"f64-full": [res.coef, res.hit, res.any_hit], "f32-wire": [mat_t, res.hit, res.any_hit],
+                    "flags-only": [res.hit, res.any_hit]}[what]
+            # chunks of the compute / push overlap: few large copies for the FP64 payload (round 1: 2 chunks
+            # at 8 GPUs), more for the smaller payloads, whose last chunk's push is what is left exposed
+            chunks = {"f64-full": args.gather_chunks, "f32-wire": args.gather_chunks_f32,
+                      "flags-only": args.gather_chunks_flags}[what]
+            g = PeerPushAllGather(B, world, rank, chunks, tmpl, streams=args.push_streams, taper={"f64-full": False, "f32-wire": "head" if world >= 4 else "tail", "flags-only": "tail"}[what])
+            nb = len(g.buffers)
 
-    def push_chunk(lo, hi):
-        view = mst.PipelineResult(push_res.coef[lo:hi], push_res.dur[lo:hi], push_res.info[lo:hi], push_res.hit[lo:hi],
-                                  push_res.any_hit[lo:hi])
-        mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
+            def chunk(lo, hi):
+                coef = g.local_slot(0, lo, hi) if what == "f64-full" else res.coef[lo:hi]
+                view = mst.PipelineResult(coef, res.dur[lo:hi], res.info[lo:hi], g.local_slot(nb - 2, lo, hi),
+                                          g.local_slot(nb - 1, lo, hi))
+                mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
+                if what == "f32-wire":
+                    mst.pack_pol_matrix(view.coef, view.dur, out=g.local_slot(0, lo, hi))
+            return g, (lambda: g.run(chunk))
+
+        def store_mode(what):
+            g = PeerStoreGather(B, world, rank, N_SEG, K_AX, S_SAMPLES, dev,
+                                mode="pol_matrix_f32" if what == "f32-wire" else "flags")
+            return g, (lambda: g.run(lambda wire: mst.pipeline_wire(wp, t, S_SAMPLES, robot, env, wire, out=res)))
+        per_traj = {"f64-full": N_SEG * K_AX * 64 + S_SAMPLES + 1, "f32-wire": N_SEG * (1 + 8 * K_AX) * 4 + S_SAMPLES + 1,
+                    "flags-only": S_SAMPLES + 1}
+        for what, how in (("f32-wire", "push"), ("f32-wire", "store"), ("flags-only", "push"), ("flags-only", "store"),
+                          ("f64-full", "push")):
+            g, fn = push_mode(what) if how == "push" else store_mode(what)
+            modes["%s/%s" % (what, how)] = {"gather": g, "step": fn, "bytes": per_traj[what]}
+    if args.gather == "f64-full":
+        args.gather_how = "push"        # the single-pass kernel's wire outputs are the float32 matrix and the flags
+    default_mode = None if world == 1 else "%s/%s" % (args.gather, args.gather_how)
 
     def make_step(mode):
         if world == 1:
             return lambda: mst.pipeline(wp, t, S_SAMPLES, robot, env, out=res)
-        if mode == "f64-full":
-            return lambda: push.run(push_chunk)
-        g = gathers[mode]
-        return lambda: g.run(lambda wire: mst.pipeline_wire(wp, t, S_SAMPLES, robot, env, wire, out=res))
+        return modes[mode]["step"]
 
-    step = make_step(args.gather)
+    step = make_step(default_mode)
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
@@ -353,57 +370,69 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     bad = int((res.info != 0).sum().item())
-    hit_rate = float(res.any_hit.float().mean().item())
+    if world > 1:   # the flags of this rank live in its slot of the gather buffer
+        g = modes[default_mode]["gather"]
+        own_any = (g.buffers["any_hit"] if isinstance(g.buffers, dict) else g.buffers[-1])[rank * B:(rank + 1) * B]
+        hit_rate = float(own_any.float().mean().item())
+    else:
+        hit_rate = float(res.any_hit.float().mean().item())
 
     # ---- N > 1: the other gather modes, strong scaling, and a check of the gathered data -------------
     scaling_modes, strong, gather_ok = None, None, None
     if world > 1:
         side_steps = max(3, args.steps // 4)
         scaling_modes = {}
-        for mode in ("f64-full", "f32-wire", "flags-only"):
-            if mode == args.gather:
+        for mode, m in modes.items():
+            if mode == default_mode:
                 ms = ms_per_step
             else:
-                fn = make_step(mode)
                 for _ in range(2):
-                    fn()
-                ms = timed(fn, side_steps) / side_steps
-            per_traj = (N_SEG * K_AX * 64 + S_SAMPLES + 1) if mode == "f64-full" else \
-                gathers[mode].bytes_per_trajectory(N_SEG, K_AX, S_SAMPLES)
+                    m["step"]()
+                ms = timed(m["step"], side_steps) / side_steps
             scaling_modes[mode] = {"ms_per_step": ms, "value": world * B / (ms * 1e-3),
-                                   "gathered_bytes_per_trajectory": per_traj,
-                                   "nvlink_in_gbs_per_gpu": (world - 1) * B * per_traj / (ms * 1e-3) / 1e9}
+                                   "gathered_bytes_per_trajectory": m["bytes"],
+                                   "nvlink_in_gbs_per_gpu": (world - 1) * B * m["bytes"] / (ms * 1e-3) / 1e9}
         # out of the timed region: every rank's slot of this rank's gathered buffers must hold that
-        # rank's results (checksums of the local results, exchanged with NCCL)
-        g = gathers["f32-wire"]
-        g.run(lambda wire: mst.pipeline_wire(wp, t, S_SAMPLES, robot, env, wire, out=res))
-        torch.cuda.synchronize()
-
+        # rank's results (checksums of the local results, exchanged with NCCL), for both data planes
         def sums(mat, hit, any_hit):
             return torch.stack([mat.view(torch.int32).to(torch.int64).sum(), hit.to(torch.int64).sum(),
                                 (hit.to(torch.int64) * torch.arange(1, S_SAMPLES + 1, device=dev)).sum(),
                                 any_hit.to(torch.int64).sum()])
-        mine = sums(mst.pack_pol_matrix(res.coef, res.dur), res.hit, res.any_hit)
-        allsums = torch.empty((world, 4), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allsums, mine.view(1, 4))
         gather_ok = True
-        for r in range(world):
-            sl = slice(r * B, (r + 1) * B)
-            got = sums(g.buffers["pol_matrix"][sl], g.buffers["hit"][sl], g.buffers["any_hit"][sl])
-            gather_ok = gather_ok and bool(torch.equal(got, allsums[r]))
+        for mode in ("f32-wire/push", "f32-wire/store"):
+            g = modes[mode]["gather"]
+            modes[mode]["step"]()
+            torch.cuda.synchronize()
+            bufs = [g.buffers["pol_matrix"], g.buffers["hit"], g.buffers["any_hit"]] if mode.endswith("store") else g.buffers
+            own = slice(rank * B, (rank + 1) * B)
+            mine = sums(bufs[0][own], bufs[1][own], bufs[2][own])
+            ref = sums(mst.pack_pol_matrix(res.coef, res.dur), bufs[1][own], bufs[2][own])
+            gather_ok = gather_ok and bool(torch.equal(mine, ref))
+            allsums = torch.empty((world, 4), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allsums, mine.view(1, 4))
+            for r in range(world):
+                sl = slice(r * B, (r + 1) * B)
+                gather_ok = gather_ok and bool(torch.equal(sums(bufs[0][sl], bufs[1][sl], bufs[2][sl]), allsums[r]))
         flag = torch.tensor([0 if gather_ok else 1], device=dev)
         dist.all_reduce(flag)
         gather_ok = int(flag.item()) == 0
         # strong scaling of configs[4]: 1,048,576 trajectories in total, sharded over the ranks
         Bs = TRAJ_PER_GPU // world
-        gs = PeerStoreGather(Bs, world, rank, N_SEG, K_AX, S_SAMPLES, dev, mode="pol_matrix_f32")
         res_s = new_result(Bs)
-        fn = lambda: gs.run(lambda wire: mst.pipeline_wire(wp[:Bs], t[:Bs], S_SAMPLES, robot, env, wire, out=res_s))
+        mat_s = torch.empty((1, N_SEG, 1 + 8 * K_AX), dtype=torch.float32, device=dev)
+        gs = PeerPushAllGather(Bs, world, rank, 2, [mat_s, res_s.hit, res_s.any_hit], streams=args.push_streams)
+
+        def strong_chunk(lo, hi):
+            view = mst.PipelineResult(res_s.coef[lo:hi], res_s.dur[lo:hi], res_s.info[lo:hi], gs.local_slot(1, lo, hi),
+                                      gs.local_slot(2, lo, hi))
+            mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
+            mst.pack_pol_matrix(view.coef, view.dur, out=gs.local_slot(0, lo, hi))
+        fn = lambda: gs.run(strong_chunk)
         for _ in range(3):
             fn()
         ms = timed(fn, args.steps) / args.steps
         strong = {"total_trajectories": Bs * world, "ms_per_step": ms, "value": Bs * world / (ms * 1e-3),
-                  "gather": "f32-wire"}
+                  "gather": "f32-wire/push"}
 
     # ---- the kernels of the step alone, timed live with CUDA events on the launching stream -----------
     stage_ms = {}
@@ -507,7 +536,9 @@ def run_ours(args):
 
     launches_per_step = lib.mst_pipeline_launch_count(B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES)
     if world > 1:
-        launches_per_step += 1      # wire patch kernel (list mode) behind mst_pipeline_wire
+        nch = {"f64-full": args.gather_chunks, "f32-wire": args.gather_chunks_f32, "flags-only": args.gather_chunks_flags}[args.gather]
+        launches_per_step = launches_per_step * nch + (nch if args.gather == "f32-wire" else 0) \
+            if args.gather_how == "push" else launches_per_step + 1   # pack kernel per chunk / wire patch kernel
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "hbm_frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "sample_collide_kernel<3> (%.0f %% of the two-launch step)" % (100 * dom_ms / step_ms),
@@ -538,7 +569,12 @@ def run_ours(args):
                                % (B, N_SEG, K_AX, S_SAMPLES, ROBOT, ENV, SEED),
                    "trajectories_per_gpu": B, "l2": "inputs+outputs %.2f GB per step >> 126 MB L2 (no flush needed)"
                    % (B * (ALG_BYTES + N_SEG * 8 + 4) / 1e9),
-                   "gather": gather_note,
+                   "gather": None if world == 1 else
+                   "%s: %s" % (default_mode, "two-launch pipeline into a symmetric buffer, copy-engine pushes to every peer, "
+                               "%d chunks" % {"f64-full": args.gather_chunks, "f32-wire": args.gather_chunks_f32,
+                                                "flags-only": args.gather_chunks_flags}[args.gather]
+                               if args.gather_how == "push" else
+                               "single-pass kernel storing through all peer pointers (mst_pipeline_wire)"),
                    "solver": "auto (condensed LDL^T; banded pivoted LU for wide duration spreads)"},
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -575,7 +611,11 @@ def main():
                     help="chunks of the overlapped all-gather (0: 4 up to 4 GPUs where the kernels still matter, "
                          "2 at 8, where few large NVLink copies win; profiles/r1_scaling.md)")
     ap.add_argument("--gather", choices=["f32-wire", "flags-only", "f64-full"], default="f32-wire",
-                    help="what the timed step gathers at N > 1 (the other two modes are timed beside it)")
+                    help="what the timed step gathers at N > 1 (the other modes are timed beside it)")
+    ap.add_argument("--gather-chunks-f32", type=int, default=3, help="tapered: 4 : 2 : 1 at 2 GPUs (compute-bound), 1 : 2 : 4 from 4 GPUs (exchange-bound)")
+    ap.add_argument("--gather-chunks-flags", type=int, default=4, help="tapered (8 : 4 : 2 : 1)")
+    ap.add_argument("--gather-how", choices=["push", "store"], default="push",
+                    help="copy-engine push behind the two-launch pipeline, or peer stores from the single-pass kernel")
     ap.add_argument("--push-streams", type=int, default=1)
     ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
     ap.add_argument("--no-cpu-baseline", action="store_true")

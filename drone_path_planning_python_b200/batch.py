@@ -149,7 +149,7 @@ def time_gradient(coef) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- a8
-def pack_pol_matrix(coef, dur) -> torch.Tensor:
+def pack_pol_matrix(coef, dur, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``coef[B, n, K, 8]``, ``dur[B, n]`` -> float32 ``[B, n, 1 + 8K]`` rows
     ``[T | x0..x7 | y0..y7 | ...]`` (reference: path_to_pol's matrix,
     scripts/drones_pols_generator.py:63-77)."""
@@ -158,7 +158,10 @@ def pack_pol_matrix(coef, dur) -> torch.Tensor:
     coef = _f64(coef, dev)
     dur = _f64(dur, dev)
     B, n, K, _ = coef.shape
-    out = torch.empty((B, n, 1 + 8 * K), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((B, n, 1 + 8 * K), dtype=torch.float32, device=dev)
+    else:
+        _check_out("out", out, (B, n, 1 + 8 * K), torch.float32, dev)
     _abi.check(lib.mst_pack_pol_matrix(_ptr(coef), _ptr(dur), B, n, K, _ptr(out), _stream_ptr()), "mst_pack_pol_matrix")
     return out
 

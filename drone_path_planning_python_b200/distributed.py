@@ -25,14 +25,29 @@ def shard_bounds(total: int, world: int, rank: int, group: int = 1) -> Tuple[int
     return lo * group, hi * group
 
 
-def chunk_plan(count: int, chunks: int, group: int = 1) -> List[Tuple[int, int]]:
+def chunk_plan(count: int, chunks: int, group: int = 1, taper=False) -> List[Tuple[int, int]]:
     """Split ``count`` local trajectories into at most ``chunks`` contiguous pieces (multiples
-    of ``group``) for the compute/gather overlap."""
+    of ``group``) for the compute/gather overlap.  ``taper`` = True / ``"tail"``: every piece half the
+    size of the one before it (8 : 4 : 2 : 1 ...), so that the push of the LAST piece — the only one
+    no later compute hides — is short (compute-bound steps).  ``"head"``: the mirror image
+    (1 : 2 : 4 ...), so that pushing starts early (exchange-bound steps: the step is then the first
+    piece's compute plus all the pushes)."""
     units = count // group
     chunks = max(1, min(chunks, units if units > 0 else 1))
+    if taper:
+        weights = [2 ** (chunks - 1 - c) for c in range(chunks)]
+        if taper == "head":
+            weights.reverse()
+        total, sizes, used = sum(weights), [], 0
+        for c, w in enumerate(weights):
+            n = units - used if c == chunks - 1 else max(1, (units * w) // total) if units - used > 0 else 0
+            n = min(n, units - used)
+            sizes.append(n)
+            used += n
+    else:
+        sizes = [units // chunks + (1 if c < units % chunks else 0) for c in range(chunks)]
     out, lo = [], 0
-    for c in range(chunks):
-        n = units // chunks + (1 if c < units % chunks else 0)
+    for n in sizes:
         out.append((lo * group, (lo + n) * group))
         lo += n
     return [p for p in out if p[1] > p[0]]
@@ -95,10 +110,10 @@ class PeerPushAllGather:
     """
 
     def __init__(self, count: int, world: int, rank: int, chunks: int, templates: Sequence[torch.Tensor],
-                 group: int = 1, streams: int = 1):
+                 group: int = 1, streams: int = 1, taper=False):
         import torch.distributed._symmetric_memory as symm
         self.count, self.world, self.rank = count, world, rank
-        self.plan = chunk_plan(count, chunks, group)
+        self.plan = chunk_plan(count, chunks, group, taper)
         self.buffers, self.handles, self.peers = [], [], []
         gname = dist.group.WORLD.group_name
         for t in templates:

@@ -109,6 +109,18 @@ def test_shard_bounds_and_chunk_plan():
 
 
 # ------------------------------------------------------------------ host build of the kernels' arithmetic
+def test_tapered_chunk_plan():
+    from drone_path_planning_python_b200.distributed import chunk_plan
+    for count, chunks, group in ((1 << 20, 4, 1), (1000, 3, 5), (7, 4, 1), (40, 1, 5), (5, 8, 1)):
+        plan = chunk_plan(count, chunks, group, taper=True)
+        assert plan[0][0] == 0 and plan[-1][1] == count
+        assert all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+        assert all((hi - lo) % group == 0 and hi > lo for lo, hi in plan)
+        sizes = [hi - lo for lo, hi in plan]
+        assert all(x >= y for x, y in zip(sizes, sizes[1:-1] + sizes[-1:])) or len(sizes) <= 2 or sizes[0] >= sizes[-1]
+    assert [hi - lo for lo, hi in chunk_plan(1500, 4, 1, taper=True)] == [800, 400, 200, 100]
+
+
 def _hostcheck():
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cu")
     out = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")

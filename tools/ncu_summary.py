@@ -81,7 +81,7 @@ def one_kernel(path, kernel, trajectories):
         dmul = get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum")
         dadd = get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
         out = {"kernel": row[head.index("Kernel Name")][:80], "trajectories_per_launch": trajectories,
-               "gpu_time_us": get("gpu__time_duration.sum", scale=False),
+               "gpu_time": "%s %s" % (row[head.index("gpu__time_duration.sum")], units[head.index("gpu__time_duration.sum")]),
                "dram_bytes_per_trajectory": dram / trajectories,
                "dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"),
                "warp_instructions_per_trajectory": (get("smsp__inst_executed.sum") or 0.0) / trajectories,
