@@ -9,7 +9,7 @@ device every call raises.
 """
 from . import _abi  # noqa: F401
 from .batch import (Mesh, PipelineResult, make_wire_targets, pipeline_wire, collide_motions, collide_pose_now, collide_poses, collide_trajectories, flat_outputs, formation_waypoints,  # noqa: F401
-                    pack_pol_matrix, pipeline, poly_derivative, poly_terms_at_t, sample_batch, snap_cost, solve_batch,
+                    pack_pol_matrix, pipeline, pol_matrix_csv, sample_now, sample_piece_now, poly_derivative, poly_terms_at_t, sample_batch, snap_cost, solve_batch,
                     time_gradient, time_power_rows)
 from .time_allocation import optimize_time_allocation  # noqa: F401
 

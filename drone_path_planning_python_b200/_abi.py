@@ -33,6 +33,9 @@ PROTOTYPES = {
     "mst_time_gradient": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p]),
     "mst_pack_pol_matrix": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            c_void_p, c_void_p]),
+    "mst_csv_stride": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "mst_format_pol_matrix_csv": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
+                                                 ctypes.c_longlong, c_void_p, c_void_p]),
     "mst_sample_batch": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_void_p, c_void_p, c_void_p]),

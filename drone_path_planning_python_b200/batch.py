@@ -166,6 +166,26 @@ def pack_pol_matrix(coef, dur, out: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+def pol_matrix_csv(matrix) -> list:
+    """float32 ``matrix[B, n, 1 + 8K]`` (``pack_pol_matrix``) -> list of ``B`` ``bytes`` objects, each the
+    file ``np.savetxt(f, matrix[b], delimiter=",")`` writes (scripts/drones_pols_generator.py:79-81),
+    byte for byte; all matrices formatted in one launch."""
+    dev = _abi.require_cuda()
+    lib = _abi.load()
+    m = matrix if isinstance(matrix, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(matrix, dtype=np.float32))
+    m = m.to(device=dev, dtype=torch.float32).contiguous()
+    if m.dim() == 2:
+        m = m[None]
+    B, n, width = m.shape
+    stride = lib.mst_csv_stride(n, width)
+    text = torch.empty((B, stride), dtype=torch.uint8, device=dev)
+    length = torch.empty((B,), dtype=torch.int32, device=dev)
+    _abi.check(lib.mst_format_pol_matrix_csv(_ptr(m), B, n, width, _ptr(text), stride, _ptr(length), _stream_ptr()),
+               "mst_format_pol_matrix_csv")
+    text_h, len_h = text.cpu().numpy(), length.cpu().numpy()
+    return [text_h[b, :len_h[b]].tobytes() for b in range(B)]
+
+
 # --------------------------------------------------------------------------- a5/a6
 def sample_batch(coef, dur, ts=None, S: Optional[int] = None, mode: str = "piecewise", deriv: int = 0,
                  return_status: bool = False):
@@ -449,3 +469,73 @@ def pipeline_wire(wp, t, S: int, robot: Mesh, env: Mesh, wire, share_time_group:
                                _stream_ptr())
     _abi.check(rc, "mst_pipeline_wire")
     return out
+
+
+# --------------------------------------------------------------------------- single evaluations
+class _SyncSlot:
+    """Per-thread staging for SINGLE evaluations through the drop-in surface (``Polynomial.eval``,
+    ``PiecewisePolynomial.eval``, ``Trajectory.eval`` called one time value at a time): inputs and
+    outputs live in pinned host memory, which the kernels read and write in place (unified
+    addressing), so a call is one launch and one stream synchronisation — no tensor allocation,
+    no staging copies."""
+
+    def __init__(self):
+        dev = _abi.require_cuda()
+        self.stream = torch.cuda.Stream(device=dev)
+        self.inp = torch.zeros(64, dtype=torch.float64).pin_memory()    # [0:32] coefficients, [32] duration, [40] t
+        self.out = torch.zeros(16, dtype=torch.float64).pin_memory()
+        self.status = torch.zeros(8, dtype=torch.uint8).pin_memory()
+        self.inp_np, self.out_np, self.status_np = self.inp.numpy(), self.out.numpy(), self.status.numpy()
+        self.p_coef = self.inp.data_ptr()
+        self.p_dur = self.inp.data_ptr() + 32 * 8
+        self.p_t = self.inp.data_ptr() + 40 * 8
+        self.p_out, self.p_status = self.out.data_ptr(), self.status.data_ptr()
+        self.inp_np[32] = 1.0
+
+
+_sync_local = __import__("threading").local()
+
+
+def _sync_slot() -> _SyncSlot:
+    slot = getattr(_sync_local, "slot", None)
+    if slot is None:
+        slot = _sync_local.slot = _SyncSlot()
+    return slot
+
+
+def sample_piece_now(coefs, t: float, deriv: int = 0) -> float:
+    """One polynomial (<= 8 ascending coefficients, host) at one time: ``Polynomial.eval``."""
+    lib = _abi.load()
+    slot = _sync_slot()
+    c = slot.inp_np
+    c[:8] = 0.0
+    c[:len(coefs)] = coefs
+    c[40] = t
+    rc = lib.mst_sample_batch(slot.p_coef, slot.p_dur, 1, 1, 1, slot.p_t, 0, 1, _abi.SAMPLE_PIECEWISE, int(deriv),
+                              slot.p_out, slot.p_status, slot.stream.cuda_stream)
+    _abi.check(rc, "mst_sample_batch")
+    slot.stream.synchronize()
+    return float(slot.out_np[0])
+
+
+def sample_now(coef_dev: torch.Tensor, dur_dev: torch.Tensor, t: float, mode: str = "piecewise", deriv: int = 0,
+               flat: bool = False):
+    """One time value against device-resident ``coef[1, n, K, 8]`` / ``dur[1, n]``: returns
+    ``(values[K] or flat outputs[13], status)`` as host numbers (``PiecewisePolynomial.eval`` /
+    ``Trajectory.eval`` one call at a time)."""
+    lib = _abi.load()
+    slot = _sync_slot()
+    slot.inp_np[40] = t
+    _, n, K, _ = coef_dev.shape
+    # the arrays may have been produced on another stream: order this stream behind it
+    slot.stream.wait_stream(torch.cuda.current_stream())
+    if flat:
+        rc = lib.mst_flat_outputs(coef_dev.data_ptr(), dur_dev.data_ptr(), 1, n, slot.p_t, 0, 1, _MODES[mode], slot.p_out,
+                                  slot.p_status, slot.stream.cuda_stream)
+        _abi.check(rc, "mst_flat_outputs")
+    else:
+        rc = lib.mst_sample_batch(coef_dev.data_ptr(), dur_dev.data_ptr(), 1, n, K, slot.p_t, 0, 1, _MODES[mode], int(deriv),
+                                  slot.p_out, slot.p_status, slot.stream.cuda_stream)
+        _abi.check(rc, "mst_sample_batch")
+    slot.stream.synchronize()
+    return slot.out_np[:13 if flat else K].copy(), int(slot.status_np[0])

@@ -45,18 +45,26 @@ class Fcl_mesh():
         """Upload the mesh; the returned object plays the role of fcl.BVHModel (:42-52)."""
         soup = _meshio.triangle_soup(self.verts, self.tris)
         self.m = _mst.Mesh(soup)
-        self.T = np.zeros(3)
-        self.q = np.array([0.0, 0.0, 0.0, 1.0])
+        self._pose = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0])   # (x, y, z, qx, qy, qz, qw)
         self.collision_object = self
         return self.m
 
     def set_transform(self, T=[0, 0, 0], q=[0, 0, 0, 1]):
         # q arrives as xyzw like in the reference, which reorders it for fcl (:54-59)
-        self.T = np.asarray(T, dtype=np.float64).reshape(3)
-        self.q = np.asarray(q, dtype=np.float64).reshape(4)
+        pose = self._pose
+        pose[0], pose[1], pose[2] = T[0], T[1], T[2]
+        pose[3], pose[4], pose[5], pose[6] = q[0], q[1], q[2], q[3]
+
+    @property
+    def T(self):
+        return self._pose[:3]
+
+    @property
+    def q(self):
+        return self._pose[3:]
 
     def pose(self):
-        return np.concatenate([self.T, self.q])
+        return self._pose
 
 
 def visualize_meshes(filenames):
@@ -87,13 +95,26 @@ class Fcl_checker():
         self.robot = Fcl_mesh(robot_mesh_file)
         self.request = None   # fcl.CollisionRequest() in the reference: default request, no contacts
         self.result = None
+        # the single query, bound once: mst_collide_pose_sync(robot, env, pose[7], 7, &hit)
+        import ctypes
+        lib = _mst._abi.load()
+        _mst._abi.require_cuda()
+        out = ctypes.c_int(-1)
+        fn, rh, eh, ref = lib.mst_collide_pose_sync, self.robot.m.handle, self.env.m.handle, ctypes.byref(out)
+
+        def query(pose, _fn=fn, _rh=rh, _eh=eh, _ref=ref, _out=out, _check=_mst._abi.check):
+            rc = _fn(_rh, _eh, pose.ctypes.data, 7, _ref)
+            if rc != 0:
+                _check(rc, "mst_collide_pose_sync")
+            return _out.value
+        self._query = query
 
     def check_collision(self, T=None, q=[0, 0, 0, 1]):
         if T is not None:
             self.robot.set_transform(T, q)
         # one launch + one stream synchronisation (mst_collide_pose_sync); fcl.collide returns the
         # number of contacts: 0 or 1 for the default request
-        return _mst.collide_pose_now(self.robot.m, self.env.m, self.robot.pose())
+        return self._query(self.robot._pose)
 
     def set_robot_transform(self, T, q=[0, 0, 0, 1]):
         self.robot.set_transform(T, q)

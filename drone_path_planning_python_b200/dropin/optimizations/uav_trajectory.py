@@ -56,8 +56,11 @@ class Polynomial:
         assert t >= 0
         if len(self.p) == 0:
             return 0.0
-        coef = _padded(self.p).reshape(1, 1, 1, _NCOEF)
-        val = float(_host(_mst.sample_batch(coef, np.ones((1, 1)), ts=np.array([float(t)])))[0, 0, 0])
+        flat = np.asarray(self.p, dtype=np.float64).reshape(-1)
+        if flat.size > _NCOEF:
+            raise NotImplementedError("polynomials above 7th order are not supported by the CUDA path")
+        # one launch + one stream synchronisation, arguments through pinned memory (sample_piece_now)
+        val = _mst.sample_piece_now(flat, float(t))
         # with (8,1)-shaped coefficients the reference's Horner loop yields a shape-(1,) array
         return np.array([val]) if self._column_shaped() else val
 
@@ -162,10 +165,10 @@ class Trajectory:
         assert t >= 0
         assert t <= self.duration
         coef, dur = self._device_arrays()
-        out, status = _mst.flat_outputs(coef, dur, ts=np.array([float(t)]), mode="trajectory", return_status=True)
-        if int(status[0, 0]) != 0:
+        row, status = _mst.sample_now(coef, dur, float(t), mode="trajectory", flat=True)
+        if status != 0:
             return None  # the reference falls off its loop (rounding of the running sum)
-        return _flat_to_output(_host(out)[0, 0])
+        return _flat_to_output(row)
 
     def eval_many(self, ts):
         """``[S, 13]`` rows ``pos vel acc omega yaw`` for many times in one launch."""
@@ -191,10 +194,20 @@ class PiecewisePolynomial():
         dur = np.asarray([float(d) for d in self.time_durations], dtype=np.float64).reshape(1, -1)
         return coef, dur
 
+    def _device_arrays(self):
+        """Device copies of the pieces, rebuilt when the piece list or a duration changes."""
+        key = (tuple(id(p.p) for p in self.pols), tuple(self.time_durations))
+        cached = getattr(self, "_dev", None)
+        if cached is None or cached[0] != key:
+            coef, dur = self._arrays()
+            dev = _mst._abi.require_cuda()
+            cached = self._dev = (key, _mst.batch._f64(coef, dev), _mst.batch._f64(dur, dev))
+        return cached[1], cached[2]
+
     def eval(self, t):
         assert t >= 0
-        coef, dur = self._arrays()
-        val = float(_host(_mst.sample_batch(coef, dur, ts=np.array([float(t)])))[0, 0, 0])
+        coef, dur = self._device_arrays()
+        val = float(_mst.sample_now(coef, dur, float(t), mode="piecewise")[0][0])
         column = self.nOfPols > 0 and isinstance(self.pols[0].p, np.ndarray) and self.pols[0].p.ndim == 2
         return np.array([val]) if column else val
 

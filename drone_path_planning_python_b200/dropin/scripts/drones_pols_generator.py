@@ -68,12 +68,29 @@ def paths_to_matrices(poses, total_duration=TOTAL_DURATION):
     return _mst.pack_pol_matrix(coef, dur).cpu().numpy()
 
 
+def paths_to_csv(poses, directory, first_id=1, total_duration=TOTAL_DURATION):
+    """Batched ``path_to_pol`` file output: ``poses[B, m, 7]`` -> ``Pol_matrix_{first_id + b}.csv`` in
+    ``directory``, each byte-identical to what ``np.savetxt(..., delimiter=",")`` writes for that
+    drone's float32 matrix; solve, packing and text formatting are one launch each for all B."""
+    matrices = paths_to_matrices(poses, total_duration)
+    files = _mst.pol_matrix_csv(matrices)
+    names = []
+    for b, blob in enumerate(files):
+        name = os.path.join(directory, "Pol_matrix_{}.csv".format(first_id + b))
+        with open(name, "wb") as fh:
+            fh.write(blob)
+        names.append(name)
+    return matrices, names
+
+
 def path_to_pol(path, cfid: int):
     print("Path received...")
     matrix = paths_to_matrices(_path_array(path)[None])[0]
 
     try:
-        np.savetxt(os.path.join(OUTPUT_DIR, "Pol_matrix_{}.csv".format(cfid)), matrix, delimiter=",")
+        # the bytes np.savetxt(file, matrix, delimiter=",") writes ('%.18e' fields), formatted on the GPU
+        with open(os.path.join(OUTPUT_DIR, "Pol_matrix_{}.csv".format(cfid)), "wb") as fh:
+            fh.write(_mst.pol_matrix_csv(matrix)[0])
     except OSError as exc:  # the reference would crash on a machine without that directory
         print("could not write Pol_matrix_{}.csv: {}".format(cfid, exc))
 

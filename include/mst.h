@@ -158,6 +158,17 @@ int mst_pack_pol_matrix(const double* coef, const double* dur, int B, int n, int
                         void* stream);
 
 /*
+ * CSV text of polynomial matrices — the file np.savetxt(name, matrix, delimiter=",") writes in
+ * path_to_pol (scripts/drones_pols_generator.py:79-81): one line per piece, `width` = 1 + 8K fields
+ * in numpy's default '%.18e' format.  Byte-identical to numpy (digits by exact integer arithmetic).
+ *   mat [B][n][width] float32  ->  text [B][stride] bytes (trajectory b's file starts at
+ *   text + b * stride and is length[b] bytes long); stride >= mst_csv_stride(n, width)
+ */
+size_t mst_csv_stride(int n, int width);
+int mst_format_pol_matrix_csv(const float* mat, int B, int n, int width, char* text, long long stride,
+                              int* length, void* stream);
+
+/*
  * Batched evaluation — Polynomial.eval / Polynomial.derivative /
  * PiecewisePolynomial.eval / Trajectory.eval
  * (src/optimizations/uav_trajectory.py:17-26,119-127,154-169).

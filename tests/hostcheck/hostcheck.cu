@@ -7,6 +7,7 @@
 
 #include "../../drone_path_planning_python_b200/csrc/collide_core.cuh"
 #include "../../drone_path_planning_python_b200/csrc/condensed_core.cuh"
+#include "../../drone_path_planning_python_b200/csrc/csv_core.cuh"
 #include "../../drone_path_planning_python_b200/csrc/mesh_image.cuh"
 
 using namespace mst;
@@ -84,6 +85,16 @@ extern "C" int hostcheck_tri_pairs(const double* tri, int N, unsigned char* out1
     const V3 Q1 = {t[9], t[10], t[11]}, Q2 = {t[12], t[13], t[14]}, Q3 = {t[15], t[16], t[17]};
     out17[i] = triangles_intersect(P1, P2, P3, Q1, Q2, Q3) ? 1 : 0;
     outi[i] = triangles_intersect_interval(P1, P2, P3, Q1, Q2, Q3) ? 1 : 0;
+  }
+  return 0;
+}
+
+// "%.18e" of float32 values: out[N][32] (zero padded), lengths[N]
+extern "C" int hostcheck_format_e18(const float* v, int N, char* out, int* lengths) {
+  for (int i = 0; i < N; ++i) {
+    char buf[32] = {0};
+    lengths[i] = format_e18(v[i], buf);
+    for (int j = 0; j < 32; ++j) out[32 * (size_t)i + j] = buf[j];
   }
   return 0;
 }

@@ -314,3 +314,52 @@ def test_mesh_level_collision_anchors_hold_for_both_restatements(golden_dir):
             assert exact[i] == 0 and pair["margin"][i] > 1.0
             seen_reference_pose = True
     assert seen_reference_pose
+
+
+def test_e18_formatter_equals_python_formatting():
+    """The kernels' '%.18e' formatter (csrc/csv_core.cuh, compiled for the host) against Python's own
+    formatting of float32 values widened to double — what np.savetxt writes for the polynomial matrix
+    (scripts/drones_pols_generator.py:79-81): random bit patterns, denormals, ties, extremes."""
+    lib = _hostcheck()
+    rng = np.random.default_rng(0)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 0.2, 0.1, 1e-45, -1e-45, 3.4028235e38, 1.17549435e-38, 9.999999e18, 1e19,
+                        1e20, 123456.789, np.inf, -np.inf, np.nan, 0.5, 2.5, 1e-10, 8388608.0, 16777216.0, 9.5, 99999.99],
+                       dtype=np.float32)
+    bits = rng.integers(0, 2 ** 32, 60000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    norm = (rng.normal(size=40000) * 10.0 ** rng.integers(-12, 12, 40000)).astype(np.float32)
+    den = rng.integers(1, 2 ** 23, 5000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    vals = np.ascontiguousarray(np.concatenate([special, bits, norm, den]).astype(np.float32))
+    N = len(vals)
+    out, ln = np.zeros((N, 32), np.uint8), np.zeros(N, np.int32)
+    lib.hostcheck_format_e18(P(vals.ctypes.data), N, P(out.ctypes.data), P(ln.ctypes.data))
+    for i in range(N):
+        assert bytes(out[i, :ln[i]]).decode() == "%.18e" % vals[i], repr(vals[i])
+
+
+def test_culled_routine_on_a_large_morton_ordered_environment():
+    """build_mesh_image on 2,450 unordered triangles (Morton ordering, block boxes) + the kernels' culled
+    mesh-mesh routine on the host == the C restatement (brute force) on every pose."""
+    from drone_path_planning_python_b200 import meshio
+    from oracle import build_oracle, collision_oracle as co
+    lib = _hostcheck()
+    rng = np.random.default_rng(5)
+    side = 36
+    xs, ys = np.linspace(-3.0, 3.0, side), np.linspace(2.0, 6.0, side)
+    z = 0.6 + 0.5 * np.sin(1.7 * xs)[:, None] * np.cos(1.3 * ys)[None, :] + 0.15 * rng.normal(size=(side, side))
+    pts = np.stack([np.broadcast_to(xs[:, None], (side, side)), np.broadcast_to(ys[None, :], (side, side)), z], axis=-1)
+    tris = []
+    for i in range(side - 1):
+        for j in range(side - 1):
+            tris += [[pts[i, j], pts[i + 1, j], pts[i + 1, j + 1]], [pts[i, j], pts[i + 1, j + 1], pts[i, j + 1]]]
+    env = np.ascontiguousarray(np.asarray(tris)[rng.permutation(len(tris))])
+    robot = np.ascontiguousarray(co.mesh_triangles(meshio.shipped_mesh("custom_triangle_robot")))
+    Pn = 3000
+    poses = np.concatenate([rng.uniform([-3.3, 1.7, -0.3], [3.3, 6.3, 1.8], (Pn, 3)), rng.uniform(-3, 3, (Pn, 1))], axis=1)
+    R, T = co.pose_matrices(poses)
+    R, T = np.ascontiguousarray(R.reshape(-1, 9)), np.ascontiguousarray(T)
+    out = np.zeros(Pn, np.uint8)
+    rc = lib.hostcheck_collide_culled(P(robot.ctypes.data), len(robot), P(env.ctypes.data), len(env), P(R.ctypes.data),
+                                      P(T.ctypes.data), Pn, 1, 1, P(out.ctypes.data))
+    assert rc >= 0
+    ref = build_oracle.c_collide_poses(robot, env, poses)
+    assert np.array_equal(out, ref) and 0.1 < ref.mean() < 0.9

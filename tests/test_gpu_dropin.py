@@ -205,6 +205,10 @@ def test_node_scripts_reproduce_the_shipped_example(dropin, golden_dir, tmp_path
     assert msg.cf_id == 1 and len(msg.poly_x) == 49 * 8 and len(msg.durations) == 49
     written = np.loadtxt(str(tmp_path / "Pol_matrix_1.csv"), delimiter=",")
     assert np.array_equal(written.astype(np.float32), matrix)
+    import io
+    buf = io.BytesIO()
+    np.savetxt(buf, matrix, delimiter=",")
+    assert open(str(tmp_path / "Pol_matrix_1.csv"), "rb").read() == buf.getvalue()      # the bytes np.savetxt writes
     assert np.allclose(matrix[:, 0], 0.2, atol=1e-7)
     ts = np.linspace(0, 9.79, 300)
     ours = mst.sample_batch(matrix[None, :, 1:].reshape(1, 49, 4, 8).astype(np.float64),
@@ -214,6 +218,37 @@ def test_node_scripts_reproduce_the_shipped_example(dropin, golden_dir, tmp_path
     assert np.abs(ours[:, 3] - theirs[:, 3]).max() < 5e-6
     many = pols.paths_to_matrices(np.stack([gen._path_array(p1), gen._path_array(p2)]))
     assert many.shape == (2, 49, 33) and np.array_equal(many[0], matrix)
+
+
+def test_csv_emitter_is_byte_identical_to_savetxt(golden_dir, tmp_path):
+    """mst_format_pol_matrix_csv against np.savetxt (scripts/drones_pols_generator.py:79-81 writes the
+    float32 matrix with numpy's default '%.18e'), on the shipped matrices (whose first line as stored in
+    the reference's own CSV files is a fixture), on random matrices with extreme magnitudes, and batched."""
+    import io
+    import drone_path_planning_python_b200 as mst
+    z = _load(golden_dir, "shipped_pol_matrices.npz")
+
+    def savetxt_bytes(mat):
+        buf = io.BytesIO()
+        np.savetxt(buf, mat, delimiter=",")
+        return buf.getvalue()
+    names = [k for k in z if not k.endswith("__first_line")]
+    mats = np.stack([z[k] for k in names])                       # [6, 49, 33] float32
+    blobs = mst.pol_matrix_csv(mats)
+    for name, mat, blob in zip(names, mats, blobs):
+        assert blob == savetxt_bytes(mat), name
+        assert blob.split(b"\n")[0].decode() == str(z[name + "__first_line"]), name    # the reference's own file
+    rng = np.random.default_rng(11)
+    wild = (rng.normal(size=(5, 7, 25)) * 10.0 ** rng.integers(-40, 38, size=(5, 7, 25))).astype(np.float32)
+    wild[0, 0, :6] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45]
+    for mat, blob in zip(wild, mst.pol_matrix_csv(wild)):
+        assert blob == savetxt_bytes(mat)
+    assert mst.pol_matrix_csv(mats[0])[0] == savetxt_bytes(mats[0])            # a single 2-D matrix
+    # the node script writes its file through the same emitter
+    coef = rng.normal(size=(2, 5, 4, 8)); dur = rng.uniform(0.1, 2, (2, 5))
+    packed = mst.pack_pol_matrix(coef, dur)
+    for b, blob in enumerate(mst.pol_matrix_csv(packed)):
+        assert blob == savetxt_bytes(packed[b].cpu().numpy())
 
 
 def test_pack_pol_matrix_matches_oracle_packing():

@@ -163,3 +163,82 @@ def test_fused_piece_lookup_equals_sampler(n, S, K):
     assert torch.equal(hit, want)
     assert torch.equal(any_hit, want.amax(dim=1))
     assert 0 < int(want.sum()) < B * S
+
+
+def _terrain(side=36, seed=5):
+    """A bumpy height field over x in [-3, 3], y in [2, 6]: 2 * (side - 1)^2 triangles (2,450 for side 36)."""
+    rng = np.random.default_rng(seed)
+    xs, ys = np.linspace(-3.0, 3.0, side), np.linspace(2.0, 6.0, side)
+    z = 0.6 + 0.5 * np.sin(1.7 * xs)[:, None] * np.cos(1.3 * ys)[None, :] + 0.15 * rng.normal(size=(side, side))
+    pts = np.stack([np.broadcast_to(xs[:, None], (side, side)), np.broadcast_to(ys[None, :], (side, side)), z], axis=-1)
+    tris = []
+    for i in range(side - 1):
+        for j in range(side - 1):
+            a, b, c, d = pts[i, j], pts[i + 1, j], pts[i + 1, j + 1], pts[i, j + 1]
+            tris.append([a, b, c])
+            tris.append([a, c, d])
+    order = rng.permutation(len(tris))          # no spatial order in the input: the library sorts
+    return np.asarray(tris)[order]
+
+
+@pytest.mark.parametrize("dim", [3, 4, 7])
+def test_large_environment_block_boxes_vs_oracle(dim):
+    """An environment of 2,450 triangles (far beyond what a CTA can stage: the mesh image stays in device
+    memory, the cursor walks the block boxes above the per-triangle boxes) against the C restatement."""
+    import drone_path_planning_python_b200 as mst
+    from oracle import build_oracle, collision_oracle as co
+    rng = np.random.default_rng(60 + dim)
+    env_tris = _terrain()
+    assert len(env_tris) >= 2000
+    robot_tris = _soup("custom_triangle_robot")
+    robot, env = mst.Mesh(robot_tris), mst.Mesh(env_tris)
+    P = 30000
+    pos = rng.uniform([-3.3, 1.7, -0.3], [3.3, 6.3, 1.8], (P, 3))
+    if dim == 3:
+        poses, oracle_poses = pos, np.concatenate([pos, np.zeros((P, 1))], axis=1)
+    elif dim == 4:
+        poses = oracle_poses = np.concatenate([pos, rng.uniform(-np.pi, np.pi, (P, 1))], axis=1)
+    else:
+        q = rng.normal(size=(P, 4))
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        poses = oracle_poses = np.concatenate([pos, q], axis=1)
+    hit = mst.collide_poses(robot, env, poses).cpu().numpy()
+    ref = build_oracle.c_collide_poses(robot_tris, env_tris, oracle_poses)
+    differ = np.flatnonzero(hit != ref)
+    assert 0.1 < ref.mean() < 0.9
+    for i in differ:           # only inside the touching band
+        _, margin = co.collide_poses(robot_tris, env_tris, oracle_poses[i:i + 1], with_margin=True)
+        assert abs(margin[0]) <= 1e-9, i
+    assert len(differ) <= 3
+    # the single synchronous query and the motion validator read the same large mesh
+    for i in range(0, 200, 7):
+        assert mst.collide_pose_now(robot, env, poses[i]) == hit[i] or i in differ
+    if dim == 4:
+        a, b = poses[:500], poses[500:1000]
+        invalid = mst.collide_motions(robot, env, a, b, 9).cpu().numpy()
+        f = (np.arange(1, 10) / 9)[None, :, None]
+        states = (a[:, None, :] + (b - a)[:, None, :] * f).reshape(-1, 4)
+        each = mst.collide_poses(robot, env, states).cpu().numpy().reshape(500, 9)
+        assert np.array_equal(invalid, each.max(axis=1))
+
+
+def test_large_environment_through_the_pipeline():
+    """Trajectories over the 2,450-triangle terrain: pipeline flags == sample, then collide_poses; the
+    single-pass kernel declines meshes it cannot stage and the two-launch pipeline takes over."""
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(8)
+    robot, env = mst.Mesh(_soup("custom_triangle_robot")), mst.Mesh(_terrain())
+    for K in (3, 4):
+        B, n, S = 400, 10, 100
+        T = rng.uniform(0.5, 2.0, (B, n))
+        t = np.concatenate([np.zeros((B, 1)), np.cumsum(T, axis=1)], axis=1)
+        wp = np.zeros((B, n + 1, K))
+        wp[:, :, :3] = rng.uniform([-2.5, 2.5, 0.3], [2.5, 5.5, 1.6], (B, 1, 3)) + np.cumsum(rng.normal(0, 0.25, (B, n + 1, 3)), axis=1)
+        if K == 4:
+            wp[:, :, 3] = np.cumsum(rng.normal(0, 0.2, (B, n + 1)), axis=1)
+        for solver in ("auto", "auto_one_pass"):
+            res = mst.pipeline(wp, t, S, robot, env, solver=solver)
+            pos = mst.sample_batch(res.coef, res.dur, S=S)
+            hit = mst.collide_poses(robot, env, pos.reshape(B * S, K)).reshape(B, S)
+            assert torch.equal(res.hit, hit) and torch.equal(res.any_hit, hit.amax(dim=1))
+        assert 0.05 < float(res.any_hit.float().mean()) < 1.0

@@ -52,6 +52,23 @@ def main():
     for _ in range(500):
         pol.eval(0.7)
     out["Polynomial.eval_us"] = (time.perf_counter() - t0) / 500 * 1e6
+    pieces = [o.Polynomial(np.random.default_rng(i).normal(size=(8, 1))) for i in range(10)]
+    pc = o.PiecewisePolynomial(pieces, [1.0] * 10)
+    for _ in range(50):
+        pc.eval(3.3)
+    t0 = time.perf_counter()
+    for i in range(500):
+        pc.eval(0.01 * i)
+    out["PiecewisePolynomial.eval_us"] = (time.perf_counter() - t0) / 500 * 1e6
+    tr = o.Trajectory()
+    tr.polynomials = [o.Polynomial4D(1.0, *[np.random.default_rng(7 * i + k).normal(size=8) for k in range(4)]) for i in range(10)]
+    tr.duration = 10.0
+    for _ in range(50):
+        tr.eval(3.3)
+    t0 = time.perf_counter()
+    for i in range(500):
+        tr.eval(0.01 * i)
+    out["Trajectory.eval_us"] = (time.perf_counter() - t0) / 500 * 1e6
     ts = np.linspace(0, 1, 4000)
     t0 = time.perf_counter()
     for _ in range(20):
