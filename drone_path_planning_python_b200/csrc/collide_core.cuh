@@ -379,6 +379,14 @@ __device__ __forceinline__ void robot_world_box(const double* pp, const double* 
   }
 }
 
+// lane-local, position only: can the robot's bounding sphere about its origin reach the environment's
+// root box?  (The sampling kernels ask this before they spend a sincos on the yaw of the sample.)
+__device__ __forceinline__ bool sphere_near_environment(const double* T, const MeshBounds& rbb, const MeshBounds& evb) {
+  const double* root = evb.root;
+  return !(T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
+           T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]);
+}
+
 // lane-local: can the robot at this pose touch the environment's root box at all?
 // (bounding sphere for rigid poses, then the robot's world box)
 template <int POSE>

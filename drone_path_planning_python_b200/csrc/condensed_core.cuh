@@ -32,6 +32,12 @@
 
 namespace mst {
 
+// Which time groups the condensed solver takes: max T / min T <= 4 (anything else goes to the pivoted
+// banded LU).  A wider rule (spread <= 12 with min T >= 0.25 s) was measured in round 2
+// (profiles/r2_condensed_spread.md): normwise it stays below 7.1e-11 of the reference's coefficients, but
+// the C^6 continuity residual of the SHORT pieces — small next to the trajectory's largest coefficients,
+// so invisible normwise — grows past what the reference's own solution shows (tests/test_gpu_fullsize.py
+// ::_check_system), so the rule was not adopted.
 #define MST_CONDENSED_MAX_SPREAD 4.0
 
 // scratch slots per group: rho[n] | factors 6*(n-1) | y 3*K*(n-1)

@@ -212,14 +212,21 @@ sample_collide_kernel(const double* __restrict__ coef, const double* __restrict_
       }
       double pp[NP];
       pp[0] = pos[0]; pp[1] = pos[1]; pp[2] = pos[2];
-      if (POSE == 1) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
+      // yaw: only samples whose bounding sphere reaches the obstacle's box need the rotation (the others are
+      // free whatever the heading); the decision is the one pose_near_environment makes first anyway
+      bool reach = true;
+      if (POSE == 1) {
+        reach = sphere_near_environment(pp, rbb, evb);
+        pp[3] = 0.0; pp[4] = 1.0;
+        if (reach) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
+      }
       if (!engine) {  // meshes the bit-mask cursors cannot hold: plain per-lane test over all pairs
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         if (POSE == 1) quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
         if (active) report((int)btl, s, robot_hits_env(R, pp, rb.tri, rb.T, ev.tri, ev.box, ev.T, evb.root, rbb.radius, true));
         continue;
       }
-      const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
+      const bool near = active && reach && pose_near_environment<POSE>(pp, rbb, evb);
       if (active && !near) {
         if (LIST) hit[btl * S + s] = 0; else hit[(size_t)b0 * S + idx] = 0;
       }

@@ -377,8 +377,15 @@ onepass_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps
         }
         double pp[NP];
         pp[0] = pos[0]; pp[1] = pos[1]; pp[2] = pos[2];
-        if (POSE == 1) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
-        const bool near = active && pose_near_environment<POSE>(pp, rbb, evb);
+        // yaw: only samples whose bounding sphere reaches the obstacle's box need the rotation (the others are
+        // free whatever the heading); the decision is the one pose_near_environment makes first anyway
+        bool reach = true;
+        if (POSE == 1) {
+          reach = sphere_near_environment(pp, rbb, evb);
+          pp[3] = 0.0; pp[4] = 1.0;
+          if (reach) sincos(pos[K - 1] * 0.5, &pp[3], &pp[4]);
+        }
+        const bool near = active && reach && pose_near_environment<POSE>(pp, rbb, evb);
         // every flag starts as 0; a queued pose that turns out to collide overwrites its byte
         if (active) const_cast<unsigned char*>(tb)[L.off_hit + (size_t)q * S + s] = 0;
         ring_push<POSE>(ring, ring_tail, near, pp, (int)(round_b0 + lo + tl), s | ((round & 0x7fff) << 16), -1, 0u, 0u);

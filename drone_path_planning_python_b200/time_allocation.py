@@ -18,7 +18,7 @@ total duration fixed.
   chosen so that no duration falls below ``min_fraction`` of the mean duration;
 * the best candidate replaces ``T`` where it lowers the cost; otherwise the problem keeps its ``T``.
 
-Allocations that push a problem onto the pivoted solver (duration spread > 4, ``mst.h``) are
+Allocations that push a problem onto the pivoted solver (wide duration spreads, ``csrc/condensed_core.cuh``) are
 handled by ``mst_solve_batch`` itself; a candidate whose solve fails counts as cost ``+inf``.
 """
 from __future__ import annotations

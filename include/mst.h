@@ -57,8 +57,9 @@ enum {
 
 /* solver selection for mst_solve_batch / mst_pipeline */
 enum {
-  MST_SOLVER_AUTO = 0,   /* condensed LDL^T where the duration spread allows it, banded
-                            LU with partial pivoting otherwise (decided per time group).
+  MST_SOLVER_AUTO = 0,   /* condensed LDL^T where the duration spread allows it (max T / min T
+                            <= 4), banded LU with partial
+                            pivoting otherwise (decided per time group).
                             Trajectories too long for the pivoted solver's on-chip band
                             (28 x 8n doubles + right-hand sides > 227 kB, n > ~120) are all
                             solved by the condensed solver, at its accuracy;

@@ -106,7 +106,7 @@ def test_auto_routes_wide_spreads_to_pivoted_solver():
     coef, lu = coef.cpu().numpy(), lu.cpu().numpy()
     assert (info.cpu().numpy() == 0).all()
     spread = T.max(axis=1) / T.min(axis=1)
-    wide = spread > 4.0
+    wide = spread > 4.0       # the dispatch rule of condensed_core.cuh
     assert wide.any() and (~wide).any()
     assert np.array_equal(coef[wide], lu[wide])  # the very same kernel produced them
     for b in range(0, B, 5):
