@@ -450,20 +450,28 @@ def run_ours(args):
     def onepass_only():
         pipeline_call(_abi.SOLVER_AUTO_ONE_PASS)
 
-    def solve_only():
-        _abi.check(lib.mst_solve_batch(wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO,
-                                       res.coef.data_ptr(), res.dur.data_ptr(), res.info.data_ptr(), ws.data_ptr(),
-                                       st), "mst_solve_batch")
+    def stage_call(stage):
+        _abi.check(lib.mst_pipeline_stage(stage, wp.data_ptr(), t.data_ptr(), B, N_SEG, K_AX, 1, _abi.SOLVER_AUTO, S_SAMPLES,
+                                          robot.handle, env.handle, res.coef.data_ptr(), res.dur.data_ptr(),
+                                          res.info.data_ptr(), res.hit.data_ptr(), res.any_hit.data_ptr(), ws.data_ptr(),
+                                          st), "mst_pipeline_stage")
 
-    def collide_only():
+    def solve_only():      # the pipeline's solver launches (far-piece bounds included)
+        stage_call(1)
+
+    def collide_only():    # the pipeline's sampling / collision launch
+        stage_call(2)
+
+    def plain_collide():   # round 1's kernel: every sample evaluated (mst_collide_trajectories)
         _abi.check(lib.mst_collide_trajectories(res.coef.data_ptr(), res.dur.data_ptr(), B, N_SEG, K_AX, S_SAMPLES,
                                                 robot.handle, env.handle, res.hit.data_ptr(), res.any_hit.data_ptr(),
                                                 st), "mst_collide_trajectories")
-    pipeline_only(); onepass_only(); solve_only(); collide_only()
+    pipeline_only(); onepass_only(); solve_only(); collide_only(); plain_collide()
     side = max(3, args.steps // 2)
-    stage_ms["pipeline, two launches (default): condensed_cols_kernel + sample_collide_kernel"] = timed(pipeline_only, side) / side
-    stage_ms["condensed_cols_kernel (+ banded_lu_kernel on the empty declined list)"] = timed(solve_only, side) / side
-    stage_ms["sample_collide_kernel"] = timed(collide_only, side) / side
+    stage_ms["pipeline, two launches (default): condensed_cols_kernel + sample_collide_cull_kernel"] = timed(pipeline_only, side) / side
+    stage_ms["condensed_cols_kernel<cull> (+ banded_lu_kernel on the empty declined list)"] = timed(solve_only, side) / side
+    stage_ms["sample_collide_cull_kernel"] = timed(collide_only, side) / side
+    stage_ms["sample_collide_kernel (no culling, mst_collide_trajectories)"] = timed(plain_collide, side) / side
     stage_ms["pipeline, single pass (MST_SOLVER_AUTO_ONE_PASS): onepass_kernel"] = timed(onepass_only, side) / side
 
     peaks = {}
@@ -477,13 +485,13 @@ def run_ours(args):
     # dominant kernel: sample_collide_kernel.  Its compulsory bytes per trajectory: coefficients and
     # durations in, per-sample flags + any-flag out; the whole step is reported beside it
     # against SURVEY §8d's ALG_BYTES.
-    dom_ms = stage_ms["sample_collide_kernel"]
-    step_ms = stage_ms["pipeline, two launches (default): condensed_cols_kernel + sample_collide_kernel"]
+    dom_ms = stage_ms["sample_collide_cull_kernel"]
+    step_ms = stage_ms["pipeline, two launches (default): condensed_cols_kernel + sample_collide_cull_kernel"]
     one_ms = stage_ms["pipeline, single pass (MST_SOLVER_AUTO_ONE_PASS): onepass_kernel"]
     dom_bytes = N_SEG * K_AX * 64 + N_SEG * 8 + S_SAMPLES + 1
     achieved = B * dom_bytes / (dom_ms * 1e-3) / 1e9
     counters = load_profile_counters()
-    c_dom, c_sol, c_one = (counters.get(k) for k in ("sample_collide_kernel", "condensed_cols_kernel", "onepass_kernel"))
+    c_dom, c_sol, c_one = (counters.get(k) for k in ("sample_collide_cull_kernel", "condensed_cols_kernel", "onepass_kernel"))
     traffic = c_dom["dram_bytes_per_trajectory"] * B if c_dom else None
     # FP64 roof: measured in this run (tools/fp64_peak.py)
     fp64 = None
@@ -541,7 +549,7 @@ def run_ours(args):
             if args.gather_how == "push" else launches_per_step + 1   # pack kernel per chunk / wire patch kernel
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "hbm_frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "sample_collide_kernel<3> (%.0f %% of the two-launch step)" % (100 * dom_ms / step_ms),
+                "kernel": "sample_collide_cull_kernel<3> (%.0f %% of the two-launch step)" % (100 * dom_ms / step_ms),
                 "alg_bytes_per_trajectory": dom_bytes, "trajectories_per_launch": B, "kernel_ms": dom_ms,
                 "kernels_ms": stage_ms,
                 "traffic_source": "profiles/r2_kernel_counters.json (ncu --set full of this command)" if c_dom else None,

@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmst.so")
 SOURCES = ["api.cu", "solve_banded_lu.cu", "solve_condensed.cu", "sample.cu", "collide.cu",
-           "formation.cu", "pipeline_fused.cu", "pipeline_onepass.cu", "csv.cu"]
+           "formation.cu", "pipeline_fused.cu", "pipeline_onepass.cu", "pipeline_cull.cu", "csv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "farcull.cuh"
 #include "mst_common.cuh"
 #include "onepass.cuh"
 
@@ -50,7 +51,11 @@ int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K
 size_t condensed_workspace_bytes(int groups);
 int launch_condensed(const double* wp, const double* t, int groups, int n, int K, int G, int force,
                      double* coef, double* dur, int* info, int* list, int* list_count,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const FarCull* cull = nullptr);
+int launch_sample_collide_cull(const double* coef, const double* dur, const unsigned* far_mask, int B, int n, int K,
+                               int S, const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
+                               cudaStream_t stream);
+bool sample_collide_cull_suits(int n, int K, int S, const mst_mesh* robot, const mst_mesh* env);
 int launch_sample(const double* coef, const double* dur, int B, int n, int K, const double* ts,
                   int ts_per_traj, int S, int mode, int deriv, double* out, uint8_t* status,
                   cudaStream_t stream);
@@ -173,9 +178,18 @@ extern "C" size_t mst_solve_workspace_bytes(int B, int n, int K, int share_time_
   return align256(condensed_workspace_bytes(B / share_time_group + 1));
 }
 
+static int solve_impl(const double* wp, const double* t, int B, int n, int K, int share_time_group, int solver,
+                      double* coef, double* dur, int* info, void* workspace, void* stream, const FarCull* cull);
+
 extern "C" int mst_solve_batch(const double* wp, const double* t, int B, int n, int K,
                                int share_time_group, int solver, double* coef, double* dur,
                                int* info, void* workspace, void* stream) {
+  return solve_impl(wp, t, B, n, K, share_time_group, solver, coef, dur, info, workspace, stream, nullptr);
+}
+
+// cull (pipeline only, may be null): the condensed solver also writes the far-piece bits (farcull.cuh)
+static int solve_impl(const double* wp, const double* t, int B, int n, int K, int share_time_group, int solver,
+                      double* coef, double* dur, int* info, void* workspace, void* stream, const FarCull* cull) {
   const int G = share_time_group;
   if (B < 0 || n < 1 || K < 1 || G < 1 || B % G != 0) return MST_ERR_INVALID;
   if (solver != MST_SOLVER_AUTO && solver != MST_SOLVER_BANDED_LU && solver != MST_SOLVER_CONDENSED)
@@ -196,7 +210,7 @@ extern "C" int mst_solve_batch(const double* wp, const double* t, int B, int n, 
   int* list_count = (int*)workspace;
   int* list = list_count + 64;
   int rc = launch_condensed(wp, t, groups, n, K, G, solver == MST_SOLVER_CONDENSED, coef, dur, info,
-                            list, list_count, st);
+                            list, list_count, st, cull);
   if (rc != MST_OK || solver == MST_SOLVER_CONDENSED) return rc;
   // groups the condensed path declined (duration spread too wide, t[0] != 0, bad input)
   return launch_banded_lu(wp, t, groups, n, K, G, list, list_count, coef, dur, info, st);
@@ -257,10 +271,18 @@ extern "C" int mst_collide_trajectories(const double* coef, const double* dur, i
   return launch_sample_collide(coef, dur, B, n, K, S, robot, env, hit, any_hit, (cudaStream_t)stream);
 }
 
+// workspace of the pipeline: the solver's (declined-group list) and, behind it, three far-piece words per
+// trajectory (farcull.cuh)
 extern "C" size_t mst_pipeline_workspace_bytes(int B, int n, int K, int share_time_group, int S) {
   (void)S;
   if (B < 0 || K < 1 || n < 1 || share_time_group < 1) return 0;
-  return mst_solve_workspace_bytes(B, n, K, share_time_group);
+  return mst_solve_workspace_bytes(B, n, K, share_time_group) + align256(sizeof(unsigned) * 3 * (size_t)B);
+}
+
+// MST_PIPELINE_NO_CULL=1 switches the far-piece culling of the two-launch pipeline off (A/B measurements)
+static bool cull_enabled() {
+  static const bool off = getenv("MST_PIPELINE_NO_CULL") != nullptr && atoi(getenv("MST_PIPELINE_NO_CULL")) != 0;
+  return !off;
 }
 
 // does the single-pass kernel take these sizes?  (mirrors launch_onepass's own checks, minus the meshes)
@@ -281,9 +303,11 @@ extern "C" int mst_pipeline_launch_count(int B, int n, int K, int share_time_gro
   return chunks * (solve + 1);                           // + fused sample/collide/any-hit
 }
 
+// stages: 0 = the whole pipeline; 1 = its solver launch(es) only; 2 = its sampling / collision launch only
+// (measurement hook: the second stage then works on what an earlier call left in coef / dur / workspace)
 static int pipeline_impl(const double* wp, const double* t, int B, int n, int K, int G, int solver, int S,
                          mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,
-                         uint8_t* any_hit, const WireTargets* wire, void* workspace, void* stream) {
+                         uint8_t* any_hit, const WireTargets* wire, void* workspace, void* stream, int stage = 0) {
   cudaStream_t st = (cudaStream_t)stream;
   const int chunk = pipeline_chunk(B, n, K, G);
   for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -317,8 +341,33 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
       if (rc != MST_ERR_TOO_LARGE) return rc;
     }
     if (wire) return MST_ERR_TOO_LARGE;   // the two-launch pipeline has no wire outputs
-    rc = mst_solve_batch(wc, tc, nb, n, K, G, solver == MST_SOLVER_AUTO_ONE_PASS ? MST_SOLVER_AUTO : solver, cc, dd,
-                         info + b0, workspace, stream);
+    const int solver2 = solver == MST_SOLVER_AUTO_ONE_PASS ? MST_SOLVER_AUTO : solver;
+    if (cull_enabled() && solver2 != MST_SOLVER_BANDED_LU && sample_collide_cull_suits(n, K, S, robot, env)) {
+      // far-piece culling: the solver bounds every piece it solves, the sampling kernel skips the far ones
+      FarCull fc;
+      for (int a = 0; a < 3; ++a) {
+        const double ext_hi = K == 3 ? robot->bounds.root[3 + a] : robot->bounds.radius;
+        const double ext_lo = K == 3 ? robot->bounds.root[a] : -robot->bounds.radius;
+        fc.lo[a] = env->bounds.root[a] - ext_hi;       // positions below this keep the robot under / before the obstacles
+        fc.hi[a] = env->bounds.root[3 + a] - ext_lo;
+      }
+      fc.mask = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + mst_solve_workspace_bytes(B, n, K, G)) +
+                (size_t)3 * b0;
+      if (stage != 2) {
+        cudaError_t e = cudaMemsetAsync(fc.mask, 0, sizeof(unsigned) * 3 * (size_t)nb, st);   // groups solved elsewhere: nothing far
+        if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+        rc = solve_impl(wc, tc, nb, n, K, G, solver2, cc, dd, info + b0, workspace, stream, &fc);
+        if (rc != MST_OK) return rc;
+      }
+      if (stage == 1) continue;
+      rc = launch_sample_collide_cull(cc, dd, fc.mask, nb, n, K, S, robot, env, hh, aa, st);
+      if (rc == MST_OK) continue;
+      if (rc != MST_ERR_TOO_LARGE) return rc;
+      rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st);
+      if (rc != MST_OK) return rc;
+      continue;
+    }
+    rc = mst_solve_batch(wc, tc, nb, n, K, G, solver2, cc, dd, info + b0, workspace, stream);
     if (rc != MST_OK) return rc;
     rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st);
     if (rc != MST_OK) return rc;
@@ -340,6 +389,21 @@ extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int
   if (!hit || !any_hit || !workspace || !wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
   return pipeline_impl(wp, t, B, n, K, G, solver, S, robot, env, coef, dur, info, hit, any_hit, nullptr, workspace,
                        stream);
+}
+
+extern "C" int mst_pipeline_stage(int stage, const double* wp, const double* t, int B, int n, int K,
+                                  int share_time_group, int solver, int S, mst_mesh_t robot, mst_mesh_t env,
+                                  double* coef, double* dur, int* info, uint8_t* hit, uint8_t* any_hit,
+                                  void* workspace, void* stream) {
+  const int G = share_time_group;
+  if (stage < 0 || stage > 2 || S < 1 || (K != 3 && K != 4) || !robot || !env || G < 1 || B < 0 || n < 1 || B % G != 0)
+    return MST_ERR_INVALID;
+  if (solver != MST_SOLVER_AUTO && solver != MST_SOLVER_CONDENSED) return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!hit || !any_hit || !workspace || !wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
+  if (!cull_enabled() || !sample_collide_cull_suits(n, K, S, robot, env)) return MST_ERR_TOO_LARGE;
+  return pipeline_impl(wp, t, B, n, K, G, solver, S, robot, env, coef, dur, info, hit, any_hit, nullptr, workspace,
+                       stream, stage);
 }
 
 extern "C" int mst_pipeline_wire(const double* wp, const double* t, int B, int n, int K, int share_time_group, int S,

@@ -7,7 +7,9 @@
 // device-side list that the banded pivoted-LU kernel consumes right after (no host sync).
 #include "condensed_core.cuh"
 #include <stdlib.h>
+#include <string.h>
 
+#include "farcull.cuh"
 #include "stage.cuh"
 
 namespace mst {
@@ -133,11 +135,13 @@ condensed_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
 // coalesced loads before use.
 constexpr int COLS_TREGS = 4, COLS_WREGS = 12;  // register tile of the input pipeline, doubles per lane
 
-template <int dummy>
+// CULL = true (pipeline, n <= 32): every lane also bounds its pieces' positions while their coefficients are
+// in registers and writes the far-piece bits of its axis (farcull.cuh) for the sampling kernel.
+template <bool CULL>
 __global__ void __launch_bounds__(128)
 condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps, int groups, int n,
                       int K, int G, int force, double* __restrict__ coef, double* __restrict__ dur,
-                      int* __restrict__ info, int* __restrict__ list, int* __restrict__ list_count) {
+                      int* __restrict__ info, int* __restrict__ list, int* __restrict__ list_count, FarCull cull) {
   extern __shared__ __align__(16) double sm[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -226,6 +230,7 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
     }
     const double* wcol = ww + ((size_t)gl * G + d) * (n + 1) * K + k;
     condensed_forward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
+    unsigned farbits = 0u;
     condensed_backward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32,
                           [&](int piece, int, const double* c, double) {
                             double2* dst = reinterpret_cast<double2*>(cd + (size_t)piece * K * MST_NCOEF);
@@ -233,7 +238,10 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
                             dst[1] = make_double2(c[2], c[3]);
                             dst[2] = make_double2(c[4], c[5]);
                             dst[3] = make_double2(c[6], c[7]);
+                            if (CULL && k < 3 && axis_far(c, tg[piece + 1] - tg[piece], cull.lo[k], cull.hi[k]))
+                              farbits |= 1u << piece;
                           });
+    if (CULL && k < 3) cull.mask[traj * 3 + k] = farbits;
     if (k == 0) info[traj] = MST_INFO_OK;
   }
 }
@@ -243,9 +251,12 @@ static size_t cols_smem_per_warp(int n, int K, int G) {
   return sizeof(double) * ((size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) * (1 + R));
 }
 
+// cull (may be null): far-piece bits for the pipeline's sampling kernel; honoured by the lane-per-column
+// kernel with n <= 32 — the caller zeroes the mask beforehand, so groups solved any other way (fallback
+// kernel, pivoted solver) simply have no far pieces
 int launch_condensed(const double* wp, const double* t, int groups, int n, int K, int G, int force,
                      double* coef, double* dur, int* info, int* list, int* list_count,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const FarCull* cull) {
   if (K > 4) {
     // more axes than the per-thread register tile: everything goes to the pivoted solver
     if (force) return MST_ERR_INVALID;
@@ -260,14 +271,18 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
     if (wpb * per_warp + 64 <= MST_MAX_SMEM) {
       const int GPW = 32 / (G * K);
       const long long sets = ((long long)groups + GPW - 1) / GPW;
-      const int rc = allow_dynamic_smem((const void*)condensed_cols_kernel<0>, wpb * per_warp);
+      const bool culling = cull != nullptr && n <= 32;
+      auto kern = culling ? condensed_cols_kernel<true> : condensed_cols_kernel<false>;
+      FarCull fc;
+      if (culling) fc = *cull; else memset(&fc, 0, sizeof(fc));
+      const int rc = allow_dynamic_smem((const void*)kern, wpb * per_warp);
       if (rc != MST_OK) return rc;
       long long blocks = (sets + wpb - 1) / wpb;
       const long long cap = (long long)MST_SM_COUNT * 16;
       if (blocks > cap) blocks = cap;
       if (blocks < 1) blocks = 1;
-      condensed_cols_kernel<0><<<(unsigned)blocks, 32 * wpb, wpb * per_warp, stream>>>(wp, t, groups, n, K, G, force, coef,
-                                                                                       dur, info, list, list_count);
+      kern<<<(unsigned)blocks, 32 * wpb, wpb * per_warp, stream>>>(wp, t, groups, n, K, G, force, coef, dur, info, list,
+                                                                   list_count, fc);
       return check_launch();
     }
   }

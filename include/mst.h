@@ -265,7 +265,10 @@ int mst_collide_trajectories(const double* coef, const double* dur, int B, int n
  * Fused pipeline: solve -> sample S uniform times -> place the robot mesh at every
  * sampled position (yaw = sampled 4th axis when K = 4, else 0) -> collide.
  * Two launches (solver, then sample + collide) or, with MST_SOLVER_AUTO_ONE_PASS, one persistent
- * kernel (see the solver enum).  Results are identical either way.
+ * kernel (see the solver enum).  In the two-launch form the solver also bounds every piece it solves
+ * (Bernstein hull of its positions) and the sampling kernel skips the pieces that provably stay clear
+ * of the obstacles' root box — their samples are flagged 0 without being evaluated.  Results are
+ * identical in all forms.
  *   inputs / coef / dur / info as mst_solve_batch
  *   hit     [B][S]  per-sample collision flag
  *   any_hit [B]     1 iff any sample of the trajectory collides
@@ -278,6 +281,17 @@ int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
                  int share_time_group, int solver, int S, mst_mesh_t robot,
                  mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,
                  uint8_t* any_hit, void* workspace, void* stream);
+
+/*
+ * Measurement hook: one stage of the default (two-launch, far-piece culling) pipeline on its own, so that
+ * a benchmark can time its kernels separately with CUDA events.  stage 1 = the solver launches (they also
+ * leave the far-piece words in `workspace`), stage 2 = the sampling / collision launch on what a stage-1
+ * call with the same arguments left behind, stage 0 = mst_pipeline.  MST_ERR_TOO_LARGE when the sizes do
+ * not take the culling pipeline (the stages are then mst_solve_batch and mst_collide_trajectories).
+ */
+int mst_pipeline_stage(int stage, const double* wp, const double* t, int B, int n, int K, int share_time_group,
+                       int solver, int S, mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur, int* info,
+                       uint8_t* hit, uint8_t* any_hit, void* workspace, void* stream);
 
 /*
  * Fused pipeline with WIRE outputs for the multi-GPU gather ("all-gather ... only for

@@ -19,6 +19,6 @@ CMD="python bench.py --traj 262144 --steps 2 --warmup 1 --no-cpu-baseline"
 timeout 300 $CMD > $OUT/${TAG}_ncu_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu1.log 2>&1
 timeout 300 $CMD > $OUT/${TAG}_ncu_plain2.log 2>&1 && \
-timeout 900 ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum --clock-control none --import-source on -k "regex:onepass_kernel|sample_collide_kernel|condensed_cols_kernel" -s 6 -c 6 -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu2.log 2>&1
+timeout 900 ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum --clock-control none --import-source on -k "regex:onepass_kernel|sample_collide_cull_kernel|condensed_cols_kernel" -s 6 -c 6 -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu2.log 2>&1
 echo "ncu rc=$?"
 ls -la $OUT | tail -20
