@@ -336,9 +336,9 @@ def run_ours(args):
                 coef = g.local_slot(0, lo, hi) if what == "f64-full" else res.coef[lo:hi]
                 view = mst.PipelineResult(coef, res.dur[lo:hi], res.info[lo:hi], g.local_slot(nb - 2, lo, hi),
                                           g.local_slot(nb - 1, lo, hi))
-                mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
-                if what == "f32-wire":
-                    mst.pack_pol_matrix(view.coef, view.dur, out=g.local_slot(0, lo, hi))
+                # the float32 matrix is written by the solver kernel straight into this rank's slot
+                mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view,
+                             pol_matrix=g.local_slot(0, lo, hi) if what == "f32-wire" else None)
             return g, (lambda: g.run(chunk))
 
         def store_mode(what):
@@ -425,8 +425,7 @@ def run_ours(args):
         def strong_chunk(lo, hi):
             view = mst.PipelineResult(res_s.coef[lo:hi], res_s.dur[lo:hi], res_s.info[lo:hi], gs.local_slot(1, lo, hi),
                                       gs.local_slot(2, lo, hi))
-            mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view)
-            mst.pack_pol_matrix(view.coef, view.dur, out=gs.local_slot(0, lo, hi))
+            mst.pipeline(wp[lo:hi], t[lo:hi], S_SAMPLES, robot, env, out=view, pol_matrix=gs.local_slot(0, lo, hi))
         fn = lambda: gs.run(strong_chunk)
         for _ in range(3):
             fn()
@@ -546,7 +545,7 @@ def run_ours(args):
     if world > 1:
         nch = {"f64-full": args.gather_chunks, "f32-wire": args.gather_chunks_f32, "flags-only": args.gather_chunks_flags}[args.gather]
         launches_per_step = launches_per_step * nch + (nch if args.gather == "f32-wire" else 0) \
-            if args.gather_how == "push" else launches_per_step + 1   # pack kernel per chunk / wire patch kernel
+            if args.gather_how == "push" else launches_per_step + 1   # list-mode matrix rows per chunk / wire patch kernel
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "hbm_frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "sample_collide_cull_kernel<3> (%.0f %% of the two-launch step)" % (100 * dom_ms / step_ms),

@@ -72,6 +72,9 @@ class WireTargets(ctypes.Structure):
                 ("row_offset", ctypes.c_longlong)]
 
 
+PROTOTYPES["mst_pipeline_packed"] = (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
 PROTOTYPES["mst_pipeline_stage"] = (ctypes.c_int, [ctypes.c_int, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p,
                                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -373,10 +373,12 @@ class PipelineResult:
 
 
 def pipeline(wp, t, S: int, robot: Mesh, env: Mesh, share_time_group: int = 1, solver: str = "auto",
-             out: Optional[PipelineResult] = None) -> PipelineResult:
+             out: Optional[PipelineResult] = None, pol_matrix: Optional[torch.Tensor] = None) -> PipelineResult:
     """Solve, sample ``S`` uniform times per trajectory, place the robot mesh at every
     sample and collision-check it against ``env``.  Returns coefficients, durations,
-    solver status, ``hit[B, S]`` and ``any_hit[B]``."""
+    solver status, ``hit[B, S]`` and ``any_hit[B]``.  ``pol_matrix`` (float32 ``[B, n, 1 + 8K]``,
+    optional): also filled with the reference's wire format (``pack_pol_matrix`` of the results),
+    written by the solver kernel itself."""
     dev = _abi.require_cuda()
     lib = _abi.load()
     wp = _f64(wp, dev)
@@ -401,6 +403,13 @@ def pipeline(wp, t, S: int, robot: Mesh, env: Mesh, share_time_group: int = 1, s
                              torch.empty((B, S), dtype=torch.uint8, device=dev),
                              torch.empty((B,), dtype=torch.uint8, device=dev))
     ws = torch.empty((max(1, lib.mst_pipeline_workspace_bytes(B, n, K, G, S)),), dtype=torch.uint8, device=dev)
+    if pol_matrix is not None:
+        _check_out("pol_matrix", pol_matrix, (B, n, 1 + 8 * K), torch.float32, dev)
+        rc = lib.mst_pipeline_packed(_ptr(wp), _ptr(t), B, n, K, G, _SOLVERS[solver], S, robot.handle, env.handle,
+                                     _ptr(out.coef), _ptr(out.dur), _ptr(out.info), _ptr(out.hit), _ptr(out.any_hit),
+                                     _ptr(pol_matrix), _ptr(ws), _stream_ptr())
+        _abi.check(rc, "mst_pipeline_packed")
+        return out
     rc = lib.mst_pipeline(_ptr(wp), _ptr(t), B, n, K, G, _SOLVERS[solver], S, robot.handle, env.handle,
                           _ptr(out.coef), _ptr(out.dur), _ptr(out.info), _ptr(out.hit), _ptr(out.any_hit),
                           _ptr(ws), _stream_ptr())

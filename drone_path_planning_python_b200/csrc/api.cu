@@ -305,9 +305,11 @@ extern "C" int mst_pipeline_launch_count(int B, int n, int K, int share_time_gro
 
 // stages: 0 = the whole pipeline; 1 = its solver launch(es) only; 2 = its sampling / collision launch only
 // (measurement hook: the second stage then works on what an earlier call left in coef / dur / workspace)
+// mat (may be null): the float32 polynomial matrix as an extra output of the two-launch pipeline
 static int pipeline_impl(const double* wp, const double* t, int B, int n, int K, int G, int solver, int S,
                          mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur, int* info, uint8_t* hit,
-                         uint8_t* any_hit, const WireTargets* wire, void* workspace, void* stream, int stage = 0) {
+                         uint8_t* any_hit, const WireTargets* wire, void* workspace, void* stream, int stage = 0,
+                         float* mat = nullptr) {
   cudaStream_t st = (cudaStream_t)stream;
   const int chunk = pipeline_chunk(B, n, K, G);
   for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -319,7 +321,7 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
     uint8_t* hh = hit ? hit + (size_t)b0 * S : nullptr;
     uint8_t* aa = any_hit ? any_hit + b0 : nullptr;
     int rc = MST_ERR_TOO_LARGE;
-    if (onepass_sizes(n, K, G, solver, S)) {
+    if (mat == nullptr && onepass_sizes(n, K, G, solver, S)) {
       int* counters = (int*)workspace;
       int* list = counters + 64;
       WireTargets wchunk;
@@ -353,11 +355,26 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
       }
       fc.mask = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + mst_solve_workspace_bytes(B, n, K, G)) +
                 (size_t)3 * b0;
+      fc.mat = mat ? mat + (size_t)b0 * n * (1 + MST_NCOEF * K) : nullptr;
       if (stage != 2) {
         cudaError_t e = cudaMemsetAsync(fc.mask, 0, sizeof(unsigned) * 3 * (size_t)nb, st);   // groups solved elsewhere: nothing far
         if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
         rc = solve_impl(wc, tc, nb, n, K, G, solver2, cc, dd, info + b0, workspace, stream, &fc);
+        if (rc == MST_ERR_TOO_LARGE && fc.mat) {   // solver kernel without the matrix output: packing pass instead
+          float* m = fc.mat;
+          fc.mat = nullptr;
+          rc = solve_impl(wc, tc, nb, n, K, G, solver2, cc, dd, info + b0, workspace, stream, &fc);
+          if (rc == MST_OK) rc = launch_pack_matrix(cc, dd, (long long)nb * n, K, m, st);
+        }
         if (rc != MST_OK) return rc;
+        if (fc.mat && solver2 == MST_SOLVER_AUTO) {   // rows of the groups the pivoted solver finished
+          WireTargets wt;
+          memset(&wt, 0, sizeof(wt));
+          wt.count = 1;
+          wt.mat[0] = fc.mat;
+          rc = launch_wire_patch(cc, dd, nullptr, nullptr, n, K, G, S, (int*)workspace + 64, (int*)workspace, &wt, st);
+          if (rc != MST_OK) return rc;
+        }
       }
       if (stage == 1) continue;
       rc = launch_sample_collide_cull(cc, dd, fc.mask, nb, n, K, S, robot, env, hh, aa, st);
@@ -371,6 +388,10 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
     if (rc != MST_OK) return rc;
     rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st);
     if (rc != MST_OK) return rc;
+    if (mat) {   // no solver-side packing on this path: the packing pass
+      rc = launch_pack_matrix(cc, dd, (long long)nb * n, K, mat + (size_t)b0 * n * (1 + MST_NCOEF * K), st);
+      if (rc != MST_OK) return rc;
+    }
   }
   return MST_OK;
 }
@@ -389,6 +410,20 @@ extern "C" int mst_pipeline(const double* wp, const double* t, int B, int n, int
   if (!hit || !any_hit || !workspace || !wp || !t || !coef || !dur || !info) return MST_ERR_INVALID;
   return pipeline_impl(wp, t, B, n, K, G, solver, S, robot, env, coef, dur, info, hit, any_hit, nullptr, workspace,
                        stream);
+}
+
+extern "C" int mst_pipeline_packed(const double* wp, const double* t, int B, int n, int K, int share_time_group,
+                                   int solver, int S, mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur,
+                                   int* info, uint8_t* hit, uint8_t* any_hit, float* pol_matrix, void* workspace,
+                                   void* stream) {
+  const int G = share_time_group;
+  if (S < 1 || (K != 3 && K != 4) || !robot || !env || G < 1 || B < 0 || n < 1 || B % G != 0) return MST_ERR_INVALID;
+  if (solver != MST_SOLVER_AUTO && solver != MST_SOLVER_BANDED_LU && solver != MST_SOLVER_CONDENSED)
+    return MST_ERR_INVALID;
+  if (B == 0) return MST_OK;
+  if (!hit || !any_hit || !workspace || !wp || !t || !coef || !dur || !info || !pol_matrix) return MST_ERR_INVALID;
+  return pipeline_impl(wp, t, B, n, K, G, solver, S, robot, env, coef, dur, info, hit, any_hit, nullptr, workspace,
+                       stream, 0, pol_matrix);
 }
 
 extern "C" int mst_pipeline_stage(int stage, const double* wp, const double* t, int B, int n, int K,

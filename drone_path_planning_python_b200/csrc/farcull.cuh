@@ -16,6 +16,10 @@ namespace mst {
 struct FarCull {
   double lo[3], hi[3];
   unsigned* mask;
+  // optional second output of the solver (null: none): the float32 polynomial matrix of path_to_pol,
+  // [trajectory][piece][1 + 8K] = [T | x0..x7 | y0..y7 | ...] (scripts/drones_pols_generator.py:63-77),
+  // written while the coefficients are in registers instead of by a packing pass over HBM
+  float* mat;
 };
 
 __host__ __device__ constexpr double bern_weight(int i, int j) {

@@ -137,7 +137,8 @@ constexpr int COLS_TREGS = 4, COLS_WREGS = 12;  // register tile of the input pi
 
 // CULL = true (pipeline, n <= 32): every lane also bounds its pieces' positions while their coefficients are
 // in registers and writes the far-piece bits of its axis (farcull.cuh) for the sampling kernel.
-template <bool CULL>
+// MAT = true: the float32 polynomial matrix rows as a second output (FarCull::mat).
+template <bool CULL, bool MAT>
 __global__ void __launch_bounds__(128)
 condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps, int groups, int n,
                       int K, int G, int force, double* __restrict__ coef, double* __restrict__ dur,
@@ -240,6 +241,12 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
                             dst[3] = make_double2(c[6], c[7]);
                             if (CULL && k < 3 && axis_far(c, tg[piece + 1] - tg[piece], cull.lo[k], cull.hi[k]))
                               farbits |= 1u << piece;
+                            if (MAT) {
+                              float* row = cull.mat + (traj * n + piece) * (size_t)(1 + MST_NCOEF * K);
+                              if (k == 0) row[0] = (float)(tg[piece + 1] - tg[piece]);
+#pragma unroll
+                              for (int e = 0; e < MST_NCOEF; ++e) row[1 + MST_NCOEF * k + e] = (float)c[e];
+                            }
                           });
     if (CULL && k < 3) cull.mask[traj * 3 + k] = farbits;
     if (k == 0) info[traj] = MST_INFO_OK;
@@ -251,9 +258,10 @@ static size_t cols_smem_per_warp(int n, int K, int G) {
   return sizeof(double) * ((size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) * (1 + R));
 }
 
-// cull (may be null): far-piece bits for the pipeline's sampling kernel; honoured by the lane-per-column
-// kernel with n <= 32 — the caller zeroes the mask beforehand, so groups solved any other way (fallback
-// kernel, pivoted solver) simply have no far pieces
+// cull (may be null): far-piece bits for the pipeline's sampling kernel (cull->mask, honoured with n <= 32;
+// the caller zeroes the mask beforehand, so groups solved any other way simply have no far pieces) and / or
+// the float32 polynomial matrix (cull->mat).  Returns MST_ERR_TOO_LARGE when a matrix is asked for and the
+// sizes go to the thread-per-group fallback kernel, which does not write it.
 int launch_condensed(const double* wp, const double* t, int groups, int n, int K, int G, int force,
                      double* coef, double* dur, int* info, int* list, int* list_count,
                      cudaStream_t stream, const FarCull* cull) {
@@ -271,10 +279,12 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
     if (wpb * per_warp + 64 <= MST_MAX_SMEM) {
       const int GPW = 32 / (G * K);
       const long long sets = ((long long)groups + GPW - 1) / GPW;
-      const bool culling = cull != nullptr && n <= 32;
-      auto kern = culling ? condensed_cols_kernel<true> : condensed_cols_kernel<false>;
+      const bool culling = cull != nullptr && cull->mask != nullptr && n <= 32;
+      const bool packing = cull != nullptr && cull->mat != nullptr;
+      auto kern = culling ? (packing ? condensed_cols_kernel<true, true> : condensed_cols_kernel<true, false>)
+                          : (packing ? condensed_cols_kernel<false, true> : condensed_cols_kernel<false, false>);
       FarCull fc;
-      if (culling) fc = *cull; else memset(&fc, 0, sizeof(fc));
+      if (cull) fc = *cull; else memset(&fc, 0, sizeof(fc));
       const int rc = allow_dynamic_smem((const void*)kern, wpb * per_warp);
       if (rc != MST_OK) return rc;
       long long blocks = (sets + wpb - 1) / wpb;
@@ -286,6 +296,7 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
       return check_launch();
     }
   }
+  if (cull != nullptr && cull->mat != nullptr) return MST_ERR_TOO_LARGE;
   const int Kc = K > 4 ? 4 : K;
   const size_t scratch_per_thread = sizeof(double) * (size_t)condensed_slots(n, Kc);
   // staged input tiles (G == 1, 16-byte aligned slices for any tile start)

@@ -47,6 +47,8 @@ class HostPipeline:
                 "done": torch.cuda.Event(),
                 "wp": torch.empty((self.chunk, n + 1, K), dtype=f64, device=dev),
                 "t": torch.empty((self.chunk // self.G, n + 1), dtype=f64, device=dev),
+                "mat": torch.empty((self.chunk, n, 1 + 8 * K), dtype=torch.float32, device=dev)
+                if wire == "pol_matrix_f32" else None,
                 "res": PipelineResult(torch.empty((self.chunk, n, K, 8), dtype=f64, device=dev),
                                       torch.empty((self.chunk, n), dtype=f64, device=dev),
                                       torch.empty((self.chunk,), dtype=torch.int32, device=dev),
@@ -99,10 +101,11 @@ class HostPipeline:
                 slot["t"][:ng].copy_(t[g0:g0 + ng], non_blocking=True)
                 r = slot["res"]
                 view = PipelineResult(r.coef[:nb], r.dur[:nb], r.info[:nb], r.hit[:nb], r.any_hit[:nb])
+                mat = slot["mat"][:nb] if self.wire == "pol_matrix_f32" else None
                 pipeline(slot["wp"][:nb], slot["t"][:ng], self.S, self.robot, self.env,
-                         share_time_group=self.G, solver=self.solver, out=view)
-                if self.wire == "pol_matrix_f32":
-                    out.coef[b0:b0 + nb].copy_(pack_pol_matrix(view.coef, view.dur), non_blocking=True)
+                         share_time_group=self.G, solver=self.solver, out=view, pol_matrix=mat)
+                if self.wire == "pol_matrix_f32":   # packed by the solver kernel itself
+                    out.coef[b0:b0 + nb].copy_(mat, non_blocking=True)
                 else:
                     out.coef[b0:b0 + nb].copy_(view.coef, non_blocking=True)
                     out.dur[b0:b0 + nb].copy_(view.dur, non_blocking=True)

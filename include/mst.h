@@ -283,6 +283,16 @@ int mst_pipeline(const double* wp, const double* t, int B, int n, int K,
                  uint8_t* any_hit, void* workspace, void* stream);
 
 /*
+ * mst_pipeline with the float32 polynomial matrix as an additional output — what path_to_pol emits per
+ * trajectory (scripts/drones_pols_generator.py:63-77): pol_matrix [B][n][1 + 8K] rows
+ * [T | x0..x7 | y0..y7 | z0..z7 (| yaw0..yaw7)].  The solver kernel writes the rows while the coefficients
+ * are in registers (no packing pass over HBM); identical to mst_pack_pol_matrix of the results.
+ */
+int mst_pipeline_packed(const double* wp, const double* t, int B, int n, int K, int share_time_group, int solver,
+                        int S, mst_mesh_t robot, mst_mesh_t env, double* coef, double* dur, int* info,
+                        uint8_t* hit, uint8_t* any_hit, float* pol_matrix, void* workspace, void* stream);
+
+/*
  * Measurement hook: one stage of the default (two-launch, far-piece culling) pipeline on its own, so that
  * a benchmark can time its kernels separately with CUDA events.  stage 1 = the solver launches (they also
  * leave the far-piece words in `workspace`), stage 2 = the sampling / collision launch on what a stage-1

@@ -158,3 +158,27 @@ def test_wire_outputs_equal_packed_results(K, G):
     anys2 = [torch.full((rows,), 9, dtype=torch.uint8, device="cuda")]
     res2 = mst.pipeline_wire(wp, t, S, robot, env, mst.make_wire_targets(None, hits2, anys2, row_offset=0), share_time_group=G)
     assert torch.equal(hits2[0][:B], res2.hit) and torch.equal(anys2[0][:B], res2.any_hit)
+
+
+@pytest.mark.parametrize("K,G", [(3, 1), (4, 1), (3, 5)])
+def test_pipeline_packed_matrix_equals_pack_of_results(K, G):
+    """mst_pipeline_packed: the float32 polynomial matrix written by the solver kernel (and, for the groups
+    the pivoted solver finishes, by the list-mode pass) == mst_pack_pol_matrix of the pipeline's results;
+    everything else identical to the plain pipeline (far-piece culling included)."""
+    import drone_path_planning_python_b200 as mst
+    rng = np.random.default_rng(100 + K + G)
+    robot, env = _meshes()
+    B, n, S = 505 * G, 10, 100
+    wp, t = _workload(rng, B, n, K, G, wide_every=6, bad=((3, "decreasing"), (40, "t0")))
+    mat = torch.full((B, n, 1 + 8 * K), -7.0, dtype=torch.float32, device="cuda")
+    res = mst.pipeline(wp, t, S, robot, env, share_time_group=G, pol_matrix=mat)
+    plain = mst.pipeline(wp, t, S, robot, env, share_time_group=G)
+    nan_safe = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+    assert nan_safe(res.coef, plain.coef) and torch.equal(res.hit, plain.hit) and torch.equal(res.info, plain.info)
+    want = mst.pack_pol_matrix(res.coef, res.dur)
+    ok = (res.info == 0)
+    assert torch.equal(mat[ok], want[ok])
+    assert nan_safe(mat, want)
+    # and the culled two-launch pipeline against the separate stages (no culling in mst_collide_trajectories)
+    coef, dur, info, hit, any_hit = _separate(mst, wp, t, S, robot, env, G)
+    assert torch.equal(plain.hit[ok], hit[ok]) and torch.equal(plain.any_hit[ok], any_hit[ok])
