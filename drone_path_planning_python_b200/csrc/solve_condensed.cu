@@ -226,6 +226,13 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
     if (cls != 0) {
       for (int i = 0; i < n; ++i)
         for (int e = 0; e < MST_NCOEF; ++e) cd[(size_t)i * K * MST_NCOEF + e] = qnan;
+      if (MAT) {   // the matrix rows of a failed trajectory: durations as they are, NaN coefficients
+        for (int i = 0; i < n; ++i) {
+          float* row = cull.mat + (traj * n + i) * (size_t)(1 + MST_NCOEF * K);
+          if (k == 0) row[0] = (float)(tg[i + 1] - tg[i]);
+          for (int e = 0; e < MST_NCOEF; ++e) row[1 + MST_NCOEF * k + e] = (float)qnan;
+        }
+      }
       if (k == 0) info[traj] = cls == 2 ? MST_INFO_DECREASING : (cls == 3 ? MST_INFO_NONFINITE : (cls == 4 ? 1 : MST_INFO_DECLINED));
       continue;
     }

@@ -12,6 +12,7 @@ tail -5 $OUT/${TAG}_pytest.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 echo "bench rc=$?"
 tail -c 1500 $OUT/${TAG}_bench.json
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; tail -c 600 $OUT/${TAG}_bench_reference.json
 timeout 120 python tools/latency_probe.py > $OUT/${TAG}_latency.json 2> $OUT/${TAG}_latency.err; cat $OUT/${TAG}_latency.json
 timeout 120 python tools/fp64_peak.py > $OUT/${TAG}_fp64.json 2>&1; cat $OUT/${TAG}_fp64.json
 kill $SMI
