@@ -320,6 +320,8 @@ def run_ours(args):
     if world > 1:
         if args.gather_chunks <= 0:
             args.gather_chunks = 4 if world <= 4 else 2
+        if args.gather_chunks_flags <= 0:
+            args.gather_chunks_flags = 1 if world <= 2 else (2 if world <= 4 else 4)
         mat_t = torch.empty((1, N_SEG, 1 + 8 * K_AX), dtype=torch.float32, device=dev)
 
         def push_mode(what):
@@ -620,7 +622,9 @@ def main():
     ap.add_argument("--gather", choices=["f32-wire", "flags-only", "f64-full"], default="f32-wire",
                     help="what the timed step gathers at N > 1 (the other modes are timed beside it)")
     ap.add_argument("--gather-chunks-f32", type=int, default=3, help="tapered: 4 : 2 : 1 at 2 GPUs (compute-bound), 1 : 2 : 4 from 4 GPUs (exchange-bound)")
-    ap.add_argument("--gather-chunks-flags", type=int, default=4, help="tapered (8 : 4 : 2 : 1)")
+    ap.add_argument("--gather-chunks-flags", type=int, default=0,
+                    help="tapered (.. 4 : 2 : 1); 0: 1 chunk at 2 GPUs, 2 at 4, 4 at 8 (a chunk costs ~0.1 ms of launch "
+                         "tails; the flags of one peer take 0.14 ms of NVLink time)")
     ap.add_argument("--gather-how", choices=["push", "store"], default="push",
                     help="copy-engine push behind the two-launch pipeline, or peer stores from the single-pass kernel")
     ap.add_argument("--push-streams", type=int, default=1)
