@@ -204,10 +204,16 @@ __host__ __device__ inline void condensed_forward(const double* __restrict__ wp,
 
 // phase 3: back sweep knot n-1 .. 1; after knot i is known piece i is complete and handed
 // to `emit(piece, k, c[8], rho_i)`; piece 0 last.  (Pieces therefore arrive in DESCENDING order.)
-template <int KC, class Emit>
+// `ends` (optional): called as ends(piece, k, w0, w1, v0, a0, j0, v1, a1, j1, rho) with the piece's two end states
+// right before its coefficients are formed (the pipeline's far-piece bound works from these).
+struct NoEndStates {
+  __host__ __device__ void operator()(int, int, double, double, double, double, double, double, double, double, double) const {}
+};
+
+template <int KC, class Emit, class Ends = NoEndStates>
 __host__ __device__ inline void condensed_backward(const double* __restrict__ wp, int wstride, int n, int K,
                                                    const double* rho, const double* fac, int fstride,
-                                                   const double* ys, int ystride, Emit&& emit) {
+                                                   const double* ys, int ystride, Emit&& emit, Ends&& ends = Ends()) {
   const int stride = fstride;
   double xv[KC], xa[KC], xj[KC];  // state at knot i+1
 #pragma unroll
@@ -238,6 +244,7 @@ __host__ __device__ inline void condensed_backward(const double* __restrict__ wp
       if (k < K) {
         const double w0 = wp[(size_t)i * wstride + k], w1 = wp[(size_t)(i + 1) * wstride + k];
         double c[MST_NCOEF];
+        ends(i, k, w0, w1, nv[k], na[k], nj[k], xv[k], xa[k], xj[k], rh);
         piece_coefficients(w0, w1 - w0, nv[k], na[k], nj[k], xv[k], xa[k], xj[k], rh, c);
         emit(i, k, c, rh);
         xv[k] = nv[k]; xa[k] = na[k]; xj[k] = nj[k];

@@ -52,4 +52,30 @@ __device__ __forceinline__ bool axis_far(const double* c, double T, double lo, d
   return (bmax + m < lo) || (bmin - m > hi);
 }
 
+// The same hull from the piece's END STATES (position, velocity, acceleration, jerk at local time 0 and T),
+// which the condensed solver holds right before it forms the coefficients: the Bernstein coefficients of a
+// degree-7 polynomial on [0, T] are
+//   b0 = w0, b1 = w0 + v0 T/7, b2 = w0 + 2 v0 T/7 + a0 T^2/42, b3 = w0 + 3 v0 T/7 + 3 a0 T^2/42 + j0 T^3/210,
+//   b7 = w1, b6 = w1 - v1 T/7, b5 = w1 - 2 v1 T/7 + a1 T^2/42, b4 = w1 - 3 v1 T/7 + 3 a1 T^2/42 - j1 T^3/210
+// — 14 FMAs instead of the 36 + 16 of the monomial route, and no cancellation (the terms are the size of the
+// motion, not of the monomial coefficients).  The evaluated polynomial is the one with the ROUNDED monomial
+// coefficients piece_coefficients() forms from these states; it differs from the exact interpolant by rounding
+// relative to those coefficients' terms (up to ~200 |w1 - w0|), i.e. ~1e-13 of the motion — the margin below is
+// 1e-9 of the piece's scale.  NaN compares false: not far.
+__device__ __forceinline__ bool axis_far_states(double w0, double w1, double v0, double a0, double j0, double v1,
+                                                double a1, double j1, double T, double lo, double hi) {
+  const double t1 = T * (1.0 / 7.0), t2 = T * T * (1.0 / 42.0), t3 = T * T * T * (1.0 / 210.0);
+  const double p1 = v0 * t1, p2 = a0 * t2, p3 = j0 * t3, q1 = v1 * t1, q2 = a1 * t2, q3 = j1 * t3;
+  const double b1 = w0 + p1, b2 = fma(2.0, p1, w0) + p2, b3 = fma(3.0, p1, w0) + fma(3.0, p2, p3);
+  const double b6 = w1 - q1, b5 = fma(-2.0, q1, w1) + q2, b4 = fma(-3.0, q1, w1) + fma(3.0, q2, -q3);
+  const double scale = fabs(w0) + fabs(w1) + 300.0 * fabs(w1 - w0) +
+                       3.0 * (fabs(p1) + fabs(q1) + fabs(p2) + fabs(q2)) + fabs(p3) + fabs(q3);
+  const double m = 1e-9 * (1.0 + scale);
+  // all eight control points on one far side (chained predicate compares: cheaper than min / max in FP64)
+  const double lo2 = lo - m, hi2 = hi + m;
+  const bool below = w0 < lo2 && b1 < lo2 && b2 < lo2 && b3 < lo2 && b4 < lo2 && b5 < lo2 && b6 < lo2 && w1 < lo2;
+  const bool above = w0 > hi2 && b1 > hi2 && b2 > hi2 && b3 > hi2 && b4 > hi2 && b5 > hi2 && b6 > hi2 && w1 > hi2;
+  return below || above;
+}
+
 }  // namespace mst

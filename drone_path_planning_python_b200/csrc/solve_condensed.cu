@@ -246,14 +246,19 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
                             dst[1] = make_double2(c[2], c[3]);
                             dst[2] = make_double2(c[4], c[5]);
                             dst[3] = make_double2(c[6], c[7]);
-                            if (CULL && k < 3 && axis_far(c, tg[piece + 1] - tg[piece], cull.lo[k], cull.hi[k]))
-                              farbits |= 1u << piece;
                             if (MAT) {
                               float* row = cull.mat + (traj * n + piece) * (size_t)(1 + MST_NCOEF * K);
                               if (k == 0) row[0] = (float)(tg[piece + 1] - tg[piece]);
 #pragma unroll
                               for (int e = 0; e < MST_NCOEF; ++e) row[1 + MST_NCOEF * k + e] = (float)c[e];
                             }
+                          },
+                          [&](int piece, int, double w0, double w1, double v0, double a0, double j0, double v1, double a1,
+                              double j1, double) {
+                            // far-piece bound from the end states (farcull.cuh)
+                            if (CULL && k < 3 &&
+                                axis_far_states(w0, w1, v0, a0, j0, v1, a1, j1, tg[piece + 1] - tg[piece], cull.lo[k], cull.hi[k]))
+                              farbits |= 1u << piece;
                           });
     if (CULL && k < 3) cull.mask[traj * 3 + k] = farbits;
     if (k == 0) info[traj] = MST_INFO_OK;
