@@ -347,12 +347,17 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
     if (cull_enabled() && solver2 != MST_SOLVER_BANDED_LU && sample_collide_cull_suits(n, K, S, robot, env)) {
       // far-piece culling: the solver bounds every piece it solves, the sampling kernel skips the far ones
       FarCull fc;
+      memset(&fc, 0, sizeof(fc));
       for (int a = 0; a < 3; ++a) {
-        const double ext_hi = K == 3 ? robot->bounds.root[3 + a] : robot->bounds.radius;
-        const double ext_lo = K == 3 ? robot->bounds.root[a] : -robot->bounds.radius;
-        fc.lo[a] = env->bounds.root[a] - ext_hi;       // positions below this keep the robot under / before the obstacles
-        fc.hi[a] = env->bounds.root[3 + a] - ext_lo;
+        fc.elo[a] = env->bounds.root[a];
+        fc.ehi[a] = env->bounds.root[3 + a];
+        fc.rlo[a] = robot->bounds.root[a];
+        fc.rhi[a] = robot->bounds.root[3 + a];
+        fc.lo[a] = fc.elo[a] - fc.rhi[a];       // K = 3: positions below this keep the robot before the obstacles
+        fc.hi[a] = fc.ehi[a] - fc.rlo[a];
       }
+      fc.radius = robot->bounds.radius;
+      fc.yaw = K == 4;
       fc.mask = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + mst_solve_workspace_bytes(B, n, K, G)) +
                 (size_t)3 * b0;
       fc.mat = mat ? mat + (size_t)b0 * n * (1 + MST_NCOEF * K) : nullptr;

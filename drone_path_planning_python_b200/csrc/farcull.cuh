@@ -14,7 +14,11 @@ namespace mst {
 // robot-extended obstacle box: piece k-axis positions below lo[k] or above hi[k] are free.
 // mask[traj * 3 + k]: bit i set when piece i is far on axis k (the sampler ORs the three words).
 struct FarCull {
-  double lo[3], hi[3];
+  double lo[3], hi[3];     // K = 3: obstacle root box widened by the robot's own box (translation only)
+  // K = 4 (the robot turns about z by the sampled yaw): obstacle root box, the robot's local box and bounding
+  // radius; the robot's reach on x / y then depends on a bound of |yaw| over the piece (axis_reach)
+  double elo[3], ehi[3], rlo[3], rhi[3], radius;
+  int yaw;
   unsigned* mask;
   // optional second output of the solver (null: none): the float32 polynomial matrix of path_to_pol,
   // [trajectory][piece][1 + 8K] = [T | x0..x7 | y0..y7 | ...] (scripts/drones_pols_generator.py:63-77),
@@ -62,20 +66,56 @@ __device__ __forceinline__ bool axis_far(const double* c, double T, double lo, d
 // coefficients piece_coefficients() forms from these states; it differs from the exact interpolant by rounding
 // relative to those coefficients' terms (up to ~200 |w1 - w0|), i.e. ~1e-13 of the motion — the margin below is
 // 1e-9 of the piece's scale.  NaN compares false: not far.
-__device__ __forceinline__ bool axis_far_states(double w0, double w1, double v0, double a0, double j0, double v1,
-                                                double a1, double j1, double T, double lo, double hi) {
+struct Hull8 { double b1, b2, b3, b4, b5, b6, m; };   // inner control points and the safety margin
+
+__device__ __forceinline__ Hull8 hull_from_states(double w0, double w1, double v0, double a0, double j0, double v1,
+                                                  double a1, double j1, double T) {
   const double t1 = T * (1.0 / 7.0), t2 = T * T * (1.0 / 42.0), t3 = T * T * T * (1.0 / 210.0);
   const double p1 = v0 * t1, p2 = a0 * t2, p3 = j0 * t3, q1 = v1 * t1, q2 = a1 * t2, q3 = j1 * t3;
-  const double b1 = w0 + p1, b2 = fma(2.0, p1, w0) + p2, b3 = fma(3.0, p1, w0) + fma(3.0, p2, p3);
-  const double b6 = w1 - q1, b5 = fma(-2.0, q1, w1) + q2, b4 = fma(-3.0, q1, w1) + fma(3.0, q2, -q3);
+  Hull8 h;
+  h.b1 = w0 + p1; h.b2 = fma(2.0, p1, w0) + p2; h.b3 = fma(3.0, p1, w0) + fma(3.0, p2, p3);
+  h.b6 = w1 - q1; h.b5 = fma(-2.0, q1, w1) + q2; h.b4 = fma(-3.0, q1, w1) + fma(3.0, q2, -q3);
   const double scale = fabs(w0) + fabs(w1) + 300.0 * fabs(w1 - w0) +
                        3.0 * (fabs(p1) + fabs(q1) + fabs(p2) + fabs(q2)) + fabs(p3) + fabs(q3);
-  const double m = 1e-9 * (1.0 + scale);
-  // all eight control points on one far side (chained predicate compares: cheaper than min / max in FP64)
-  const double lo2 = lo - m, hi2 = hi + m;
-  const bool below = w0 < lo2 && b1 < lo2 && b2 < lo2 && b3 < lo2 && b4 < lo2 && b5 < lo2 && b6 < lo2 && w1 < lo2;
-  const bool above = w0 > hi2 && b1 > hi2 && b2 > hi2 && b3 > hi2 && b4 > hi2 && b5 > hi2 && b6 > hi2 && w1 > hi2;
+  h.m = 1e-9 * (1.0 + scale);
+  return h;
+}
+
+// bound of |value| over the piece (used on the yaw axis); NaN propagates as +inf-like "unknown"
+__device__ __forceinline__ double hull_max_abs(double w0, double w1, const Hull8& h) {
+  const double a = fmax(fmax(fmax(fabs(w0), fabs(h.b1)), fmax(fabs(h.b2), fabs(h.b3))),
+                        fmax(fmax(fabs(h.b4), fabs(h.b5)), fmax(fabs(h.b6), fabs(w1)))) + h.m;
+  return a == a ? a : 1e300;
+}
+
+// Reach of the turning robot on axis k (0: x, 1: y, 2: z) when |yaw| <= t over the piece: the world box of the
+// local box [rlo, rhi] rotated about z by an angle of at most t lies within [rlo_k - d, rhi_k + d] with
+// d = |own|max * t^2 / 2 + |other|max * t on x / y (1 - cos t <= t^2 / 2, |sin t| <= t), d = 0 on z — and within
+// the bounding radius in any case.  The widened obstacle box follows.
+__device__ __forceinline__ void axis_reach(const FarCull& c, int k, double t, double* lo, double* hi) {
+  double ext_lo = c.rlo[k], ext_hi = c.rhi[k];
+  if (k < 2) {
+    const double own = fmax(fabs(c.rlo[k]), fabs(c.rhi[k])), oth = fmax(fabs(c.rlo[1 - k]), fabs(c.rhi[1 - k]));
+    const double d = own * (0.5 * t * t) + oth * t;
+    ext_lo = fmax(-c.radius, ext_lo - d);
+    ext_hi = fmin(c.radius, ext_hi + d);
+  }
+  *lo = c.elo[k] - ext_hi;   // positions below this keep the robot before the obstacles on this axis
+  *hi = c.ehi[k] - ext_lo;
+}
+
+// all eight control points on one far side (chained predicate compares: cheaper than min / max in FP64)
+__device__ __forceinline__ bool hull_far(double w0, double w1, const Hull8& h, double lo, double hi) {
+  const double lo2 = lo - h.m, hi2 = hi + h.m;
+  const bool below = w0 < lo2 && h.b1 < lo2 && h.b2 < lo2 && h.b3 < lo2 && h.b4 < lo2 && h.b5 < lo2 && h.b6 < lo2 && w1 < lo2;
+  const bool above = w0 > hi2 && h.b1 > hi2 && h.b2 > hi2 && h.b3 > hi2 && h.b4 > hi2 && h.b5 > hi2 && h.b6 > hi2 && w1 > hi2;
   return below || above;
+}
+
+__device__ __forceinline__ bool axis_far_states(double w0, double w1, double v0, double a0, double j0, double v1,
+                                                double a1, double j1, double T, double lo, double hi) {
+  const Hull8 h = hull_from_states(w0, w1, v0, a0, j0, v1, a1, j1, T);
+  return hull_far(w0, w1, h, lo, hi);
 }
 
 }  // namespace mst

@@ -214,6 +214,7 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
       }
     }
     cls = __shfl_sync(FULL, cls, lane_used ? gl * R : 0);
+    const unsigned solving = __ballot_sync(FULL, mine && cls == 0);   // the lanes that run the sweeps below
     __syncwarp();
     if (!mine) continue;
     const size_t traj = (size_t)g * G + d;
@@ -256,9 +257,17 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
                           [&](int piece, int, double w0, double w1, double v0, double a0, double j0, double v1, double a1,
                               double j1, double) {
                             // far-piece bound from the end states (farcull.cuh)
-                            if (CULL && k < 3 &&
-                                axis_far_states(w0, w1, v0, a0, j0, v1, a1, j1, tg[piece + 1] - tg[piece], cull.lo[k], cull.hi[k]))
-                              farbits |= 1u << piece;
+                            if (!CULL) return;
+                            const Hull8 h = hull_from_states(w0, w1, v0, a0, j0, v1, a1, j1, tg[piece + 1] - tg[piece]);
+                            double lo = cull.lo[k < 3 ? k : 0], hi = cull.hi[k < 3 ? k : 0];
+                            if (cull.yaw) {
+                              // the robot turns by the sampled yaw (4th axis): its lane bounds |yaw| over the piece,
+                              // the position lanes of the trajectory widen the obstacle box by the robot's reach
+                              const double mine_abs = k == 3 ? hull_max_abs(w0, w1, h) : 0.0;
+                              const double t = __shfl_sync(solving, mine_abs, lane - k + 3);
+                              if (k < 3) axis_reach(cull, k, t, &lo, &hi);
+                            }
+                            if (k < 3 && hull_far(w0, w1, h, lo, hi)) farbits |= 1u << piece;
                           });
     if (CULL && k < 3) cull.mask[traj * 3 + k] = farbits;
     if (k == 0) info[traj] = MST_INFO_OK;
