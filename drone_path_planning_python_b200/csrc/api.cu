@@ -356,7 +356,7 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
         fc.lo[a] = fc.elo[a] - fc.rhi[a];       // K = 3: positions below this keep the robot before the obstacles
         fc.hi[a] = fc.ehi[a] - fc.rlo[a];
       }
-      fc.radius = robot->bounds.radius;
+      fc.radius = robot->bounds.rxy;
       fc.yaw = K == 4;
       fc.mask = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + mst_solve_workspace_bytes(B, n, K, G)) +
                 (size_t)3 * b0;

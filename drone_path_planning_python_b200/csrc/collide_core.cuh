@@ -326,9 +326,22 @@ constexpr int COLLIDE_MIN_LANES = 12; // undecided poses a drain needs to run an
 
 template <int POSE> struct PoseDim { static constexpr int N = POSE == 0 ? 3 : (POSE == 1 ? 5 : 7); };
 
+// yaw poses: R = Rz(yaw) = [[c, -s, 0], [s, c, 0], [0, 0, 1]] with c = 1 - 2 z^2, s = 2 z w of the half-angle pair
+// (z, w) = (sin, cos)(yaw / 2) — the entries quat_to_matrix(0, 0, z, w) computes; the specialised forms below
+// leave out the products with the structural zeros and ones (same values, fewer FP64 instructions).
+struct Yaw { double c, s; };
+__device__ __forceinline__ Yaw yaw_of(const double* pp) { return {1.0 - 2.0 * (pp[3] * pp[3]), 2.0 * (pp[3] * pp[4])}; }
+// R v + T
+__device__ __forceinline__ V3 xform_yaw(const Yaw& y, const double* T, const double* v) {
+  return {y.c * v[0] - y.s * v[1] + T[0], y.s * v[0] + y.c * v[1] + T[1], v[2] + T[2]};
+}
+
 template <int POSE>
 __device__ __forceinline__ void pose_rotation(const double* pp, double* R) {
-  if (POSE == 1) quat_to_matrix(0.0, 0.0, pp[3], pp[4], R);
+  if (POSE == 1) {
+    const Yaw y = yaw_of(pp);
+    R[0] = y.c; R[1] = -y.s; R[2] = 0.0; R[3] = y.s; R[4] = y.c; R[5] = 0.0; R[6] = 0.0; R[7] = 0.0; R[8] = 1.0;
+  }
   if (POSE == 2) quat_to_matrix(pp[3], pp[4], pp[5], pp[6], R);
 }
 
@@ -370,6 +383,13 @@ __device__ __forceinline__ void robot_world_box(const double* pp, const double* 
     const double h0 = 0.5 * (rbb.root[3] - rbb.root[0]), h1 = 0.5 * (rbb.root[4] - rbb.root[1]),
                  h2 = 0.5 * (rbb.root[5] - rbb.root[2]);
     const double pad = 1e-12 * (rbb.radius + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
+    if (POSE == 1) {   // rotation about z: R = [[c, -s, 0], [s, c, 0], [0, 0, 1]] (c = R[0], s = R[3])
+      const double c = R[0], sn = R[3];
+      const double w0 = c * c0 - sn * c1 + T[0], w1 = sn * c0 + c * c1 + T[1], w2 = c2 + T[2];
+      const double e0 = fabs(c) * h0 + fabs(sn) * h1 + pad, e1 = fabs(sn) * h0 + fabs(c) * h1 + pad, e2 = h2 + pad;
+      lo[0] = w0 - e0; hi[0] = w0 + e0; lo[1] = w1 - e1; hi[1] = w1 + e1; lo[2] = w2 - e2; hi[2] = w2 + e2;
+      return;
+    }
     for (int a = 0; a < 3; ++a) {
       const double w = R[3 * a] * c0 + R[3 * a + 1] * c1 + R[3 * a + 2] * c2 + T[a];
       const double ext = fabs(R[3 * a]) * h0 + fabs(R[3 * a + 1]) * h1 + fabs(R[3 * a + 2]) * h2 + pad;
@@ -381,10 +401,11 @@ __device__ __forceinline__ void robot_world_box(const double* pp, const double* 
 
 // lane-local, position only: can the robot's bounding sphere about its origin reach the environment's
 // root box?  (The sampling kernels ask this before they spend a sincos on the yaw of the sample.)
+// For a rotation about z (the yaw poses) the bound is a cylinder: planar radius on x / y, the mesh's own z range.
 __device__ __forceinline__ bool sphere_near_environment(const double* T, const MeshBounds& rbb, const MeshBounds& evb) {
   const double* root = evb.root;
-  return !(T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
-           T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]);
+  return !(T[0] + rbb.rxy < root[0] || T[0] - rbb.rxy > root[3] || T[1] + rbb.rxy < root[1] ||
+           T[1] - rbb.rxy > root[4] || T[2] + rbb.root[5] < root[2] || T[2] + rbb.root[2] > root[5]);
 }
 
 // lane-local: can the robot at this pose touch the environment's root box at all?
@@ -396,9 +417,7 @@ __device__ __forceinline__ bool pose_near_environment(const double* pp, const Me
   // bounding sphere first for rotated poses (cheaper than rotating the box); a translated box
   // is exact and just as cheap, and POSE 2 takes whatever quaternion the caller gave (maybe not
   // unit), so neither uses the sphere
-  if (POSE == 1 && (T[0] + rbb.radius < root[0] || T[0] - rbb.radius > root[3] || T[1] + rbb.radius < root[1] ||
-                    T[1] - rbb.radius > root[4] || T[2] + rbb.radius < root[2] || T[2] - rbb.radius > root[5]))
-    return false;
+  if (POSE == 1 && !sphere_near_environment(T, rbb, evb)) return false;
   double R[9], lo[3], hi[3];
   pose_rotation<POSE>(pp, R);
   robot_world_box<POSE>(pp, R, rbb, lo, hi);
@@ -546,9 +565,15 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const double* q = j == 0 ? pl : ed + 4 * (j - 1);
-              m[j][0] = R[0] * q[0] + R[3] * q[1] + R[6] * q[2];
-              m[j][1] = R[1] * q[0] + R[4] * q[1] + R[7] * q[2];
-              m[j][2] = R[2] * q[0] + R[5] * q[1] + R[8] * q[2];
+              if (POSE == 1) {   // R^T q for a rotation about z
+                m[j][0] = R[0] * q[0] + R[3] * q[1];
+                m[j][1] = R[0] * q[1] - R[3] * q[0];
+                m[j][2] = q[2];
+              } else {
+                m[j][0] = R[0] * q[0] + R[3] * q[1] + R[6] * q[2];
+                m[j][1] = R[1] * q[0] + R[4] * q[1] + R[7] * q[2];
+                m[j][2] = R[2] * q[0] + R[5] * q[1] + R[8] * q[2];
+              }
             }
             for (int v = 0; v < rb.V; ++v) {
               const double* p = rb.vert + 3 * v;
@@ -577,6 +602,9 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
         P1 = {pr[0] + pp[0], pr[1] + pp[1], pr[2] + pp[2]};
         P2 = {pr[3] + pp[0], pr[4] + pp[1], pr[5] + pp[2]};
         P3 = {pr[6] + pp[0], pr[7] + pp[1], pr[8] + pp[2]};
+      } else if (POSE == 1) {
+        const Yaw y = {R[0], R[3]};
+        P1 = xform_yaw(y, pp, pr); P2 = xform_yaw(y, pp, pr + 3); P3 = xform_yaw(y, pp, pr + 6);
       } else {
         P1 = xform(R, pp, pr); P2 = xform(R, pp, pr + 3); P3 = xform(R, pp, pr + 6);
       }

@@ -17,7 +17,7 @@ struct FarCull {
   double lo[3], hi[3];     // K = 3: obstacle root box widened by the robot's own box (translation only)
   // K = 4 (the robot turns about z by the sampled yaw): obstacle root box, the robot's local box and bounding
   // radius; the robot's reach on x / y then depends on a bound of |yaw| over the piece (axis_reach)
-  double elo[3], ehi[3], rlo[3], rhi[3], radius;
+  double elo[3], ehi[3], rlo[3], rhi[3], radius;   // radius: planar (x, y) radius of the robot about its z axis
   int yaw;
   unsigned* mask;
   // optional second output of the solver (null: none): the float32 polynomial matrix of path_to_pol,

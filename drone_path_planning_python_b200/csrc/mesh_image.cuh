@@ -97,6 +97,7 @@ inline void* build_mesh_image(const double* tri_in, int T, MeshLayout* layout, M
   memcpy(iidx, idx, sizeof(int) * 3 * (size_t)T);
   for (int k = 0; k < 3; ++k) { bounds->root[k] = 1e300; bounds->root[3 + k] = -1e300; }
   bounds->radius = 0.0;
+  bounds->rxy = 0.0;
   for (int t = 0; t < T; ++t) {
     double* box = ibox + 6 * t;
     for (int k = 0; k < 3; ++k) { box[k] = 1e300; box[3 + k] = -1e300; }
@@ -112,6 +113,9 @@ inline void* build_mesh_image(const double* tri_in, int T, MeshLayout* layout, M
       // rounded up a little: the sphere cull must stay conservative
       const double r = sqrt(r2) * (1.0 + 1e-12) + 1e-300;
       if (r > bounds->radius) bounds->radius = r;
+      const double vx = tri[9 * t + 3 * c], vy = tri[9 * t + 3 * c + 1];
+      const double rp = sqrt(vx * vx + vy * vy) * (1.0 + 1e-12) + 1e-300;
+      if (rp > bounds->rxy) bounds->rxy = rp;
       if (idx[3 * t + c] < 64) mk |= 1ull << idx[3 * t + c];
     }
     imask[t] = mk;

@@ -138,6 +138,7 @@ __host__ __device__ __forceinline__ MeshView mesh_view(const void* base, const M
 struct MeshBounds {
   double root[6];   // AABB in the mesh's own frame
   double radius;    // max |vertex|, rounded up: bound of the mesh under any rotation about its origin
+  double rxy;       // max sqrt(x^2 + y^2) over the vertices, rounded up: bound on x / y under any rotation about z
 };
 
 // host-side record behind the opaque mst_mesh_t handle
