@@ -151,7 +151,7 @@ def cpu_baseline(wp_np, t_np, per_core):
     arm.close()
     one = CpuArm(1)
     one.run(wp_np[:1], t_np[:1])
-    n1 = max(4, per_core)
+    n1 = max(4, 2 * per_core)
     secs1 = one.run(wp_np[:n1], t_np[:n1])
     one.close()
     what = ("unmodified reference package (oracle/_ref/optimizations: calculate_trajectory1D x %d axes, "
@@ -602,7 +602,7 @@ def run_ours(args):
         line["strong_scaling"] = strong
 
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wp_np, t_np, 4 if args.quick else 32)
+        line["cpu_baseline"] = cpu_baseline(wp_np, t_np, 4 if args.quick else 128)   # ~15-20 s of CPU work in all
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
