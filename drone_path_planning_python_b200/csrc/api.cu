@@ -47,7 +47,9 @@ int allow_dynamic_smem(const void* kernel, size_t dynamic_bytes) {
 // kernels' host launchers (one per .cu file)
 size_t banded_lu_smem_per_warp(int n, int R);
 int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K, int G, const int* list,
-                     const int* list_count, double* coef, double* dur, int* info, cudaStream_t stream);
+                     const int* list_count, double* coef, double* dur, int* info, double* scratch,
+                     cudaStream_t stream);
+size_t banded_lu_scratch_bytes(int groups, int n, int R);
 size_t condensed_workspace_bytes(int groups);
 int launch_condensed(const double* wp, const double* t, int groups, int n, int K, int G, int force,
                      double* coef, double* dur, int* info, int* list, int* list_count,
@@ -172,10 +174,17 @@ extern "C" int mst_pack_pol_matrix(const double* coef, const double* dur, int B,
   return launch_pack_matrix(coef, dur, (long long)B * n, K, out, (cudaStream_t)stream);
 }
 
+// solver workspace: [counters (64 ints) | list of the groups handed to the pivoted solver] [its scratch
+// for the finished columns of U]
+static size_t solve_list_bytes(int groups) { return align256(condensed_workspace_bytes(groups + 1)); }
+static double* lu_scratch(void* workspace, int groups) {
+  return workspace ? reinterpret_cast<double*>(static_cast<char*>(workspace) + solve_list_bytes(groups)) : nullptr;
+}
+
 extern "C" size_t mst_solve_workspace_bytes(int B, int n, int K, int share_time_group) {
-  (void)n; (void)K;
-  if (B < 0 || share_time_group < 1) return 0;
-  return align256(condensed_workspace_bytes(B / share_time_group + 1));
+  if (B < 0 || n < 1 || K < 1 || share_time_group < 1) return 0;
+  const int groups = B / share_time_group;
+  return solve_list_bytes(groups) + align256(banded_lu_scratch_bytes(groups, n, share_time_group * K));
 }
 
 static int solve_impl(const double* wp, const double* t, int B, int n, int K, int share_time_group, int solver,
@@ -204,16 +213,16 @@ static int solve_impl(const double* wp, const double* t, int B, int n, int K, in
   // solver alone, and a group it has to decline is reported through info[] (MST_INFO_DECLINED /
   // singular) instead of being solved
   if (!banded_fits && solver == MST_SOLVER_AUTO) solver = MST_SOLVER_CONDENSED;
-  if (solver == MST_SOLVER_BANDED_LU)
-    return launch_banded_lu(wp, t, groups, n, K, G, nullptr, nullptr, coef, dur, info, st);
   if (!workspace) return MST_ERR_INVALID;
+  if (solver == MST_SOLVER_BANDED_LU)
+    return launch_banded_lu(wp, t, groups, n, K, G, nullptr, nullptr, coef, dur, info, lu_scratch(workspace, groups), st);
   int* list_count = (int*)workspace;
   int* list = list_count + 64;
   int rc = launch_condensed(wp, t, groups, n, K, G, solver == MST_SOLVER_CONDENSED, coef, dur, info,
                             list, list_count, st, cull);
   if (rc != MST_OK || solver == MST_SOLVER_CONDENSED) return rc;
   // groups the condensed path declined (duration spread too wide, t[0] != 0, bad input)
-  return launch_banded_lu(wp, t, groups, n, K, G, list, list_count, coef, dur, info, st);
+  return launch_banded_lu(wp, t, groups, n, K, G, list, list_count, coef, dur, info, lu_scratch(workspace, groups), st);
 }
 
 extern "C" int mst_sample_batch(const double* coef, const double* dur, int B, int n, int K,
@@ -330,7 +339,7 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
                           wire ? &wchunk : nullptr, st);
       if (rc == MST_OK) {
         // groups the condensed path must not take: pivoted solve, then their samples (list mode)
-        rc = launch_banded_lu(wc, tc, nb / G, n, K, G, list, counters, cc, dd, info + b0, st);
+        rc = launch_banded_lu(wc, tc, nb / G, n, K, G, list, counters, cc, dd, info + b0, lu_scratch(workspace, nb / G), st);
         if (rc != MST_OK) return rc;
         rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st, list, counters, G);
         if (rc != MST_OK) return rc;

@@ -1,38 +1,64 @@
-// Robust solver: the reference's own 8n x 8n system, assembled in band storage in
-// shared memory and factorised by banded LU with partial pivoting, one warp per time
-// group (one matrix, R = G*K right-hand sides).
+// Robust solver: the reference's own 8n x 8n system factorised by banded LU with partial pivoting,
+// one warp per time group (one matrix, R = G*K right-hand sides).
 //
 // Replaces calculate_trajectory1D (src/optimizations/calculatingTrajectories.py:37-197)
 // including its np.linalg.solve (:137).  The row layout follows :65-128 exactly
 //  so pivoting sees the matrix LAPACK dgesv sees (entries t^k are formed by repeated
 // multiplication here, by libm pow in the reference: equal to a few ulps, not always bitwise); the band is
-// kl = 10 below / ku = 7 above the diagonal (ku = 5 when t[0] == 0, the start rows then
-// being diagonal).  `A` never exists in HBM: it is built from the n durations in shared
-// memory, factorised there, and only the 8 coefficients per piece and axis leave.
-#include "mst_common.cuh"
+// kl = 10 below / ku = 7 above the diagonal.  `A` never exists in HBM, and only a window of it exists at
+// all: banded_core.cuh holds the arithmetic and the storage scheme (window ring in shared memory,
+// finished columns of U in an L2-resident per-warp scratch, untouched columns recomputed from the
+// durations when they enter the window).
+#include "banded_core.cuh"
 
 namespace mst {
 
-constexpr int KL = 10;
-constexpr int KU = 7;
-constexpr int KV = KL + KU;          // upper bandwidth after fill-in
-constexpr int LD = 2 * KL + KU + 1;  // 28 doubles per band column (LD-1 odd: row walks are bank-conflict free)
+constexpr int BANDED_WARPS = 4;        // warps (time groups in flight) per CTA
+constexpr int BANDED_MIN_CTAS = 6;     // resident CTAs the register bound keeps possible (80 registers)
+constexpr int BANDED_WARPS_PER_SM = BANDED_WARPS * BANDED_MIN_CTAS;
 
-__host__ size_t banded_lu_smem_per_warp(int n, int R) {
-  const size_t N = (size_t)MST_NCOEF * n;
-  return sizeof(double) * ((size_t)LD * N + (size_t)R * N + (size_t)n);
+__host__ size_t banded_lu_smem_per_warp(int n, int R) { return sizeof(double) * band_warp_doubles(n, R); }
+
+struct BandedPlan {
+  int warps;        // per CTA
+  size_t smem;      // dynamic shared memory per CTA
+  int ctas_per_sm;  // resident CTAs the shared memory and the 64-register bound allow
+};
+
+// 0 warps: one group does not fit an SM's shared memory
+__host__ static BandedPlan banded_plan(int n, int R) {
+  BandedPlan p{BANDED_WARPS, 0, 0};
+  const size_t per_warp = banded_lu_smem_per_warp(n, R);
+  const size_t table = sizeof(double) * BAND_TABLE_DOUBLES;
+  while (p.warps > 1 && p.warps * per_warp + table > MST_MAX_SMEM) p.warps >>= 1;
+  p.smem = p.warps * per_warp + table;
+  if (p.smem > MST_MAX_SMEM) { p.warps = 0; return p; }
+  const size_t sm_total = 228 * 1024, cta_reserve = 1024;
+  p.ctas_per_sm = (int)(sm_total / (p.smem + cta_reserve));
+  if (p.ctas_per_sm > BANDED_WARPS_PER_SM / p.warps) p.ctas_per_sm = BANDED_WARPS_PER_SM / p.warps;
+  if (p.ctas_per_sm < 1) p.ctas_per_sm = 1;
+  return p;
 }
 
-// element (row, col) of the band lives at AB[col*LD + KV + row - col]
-__device__ __forceinline__ void band_set(double* AB, int row, int col, double v) {
-  AB[col * LD + KV + row - col] = v;
+__host__ static long long banded_grid(const BandedPlan& p, int groups) {
+  long long blocks = ((long long)groups + p.warps - 1) / p.warps;
+  const long long cap = (long long)MST_SM_COUNT * p.ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : blocks;
 }
 
-__global__ void __launch_bounds__(512)
+// device scratch for the finished columns of U: one slab of 18 x 8n doubles per warp of the grid
+__host__ size_t banded_lu_scratch_bytes(int groups, int n, int R) {
+  const BandedPlan p = banded_plan(n, R);
+  if (p.warps == 0 || groups < 1) return 0;
+  return sizeof(double) * (size_t)banded_grid(p, groups) * p.warps * UROWS * MST_NCOEF * n;
+}
+
+__global__ void __launch_bounds__(BANDED_WARPS * 32, BANDED_MIN_CTAS)
 banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps,
                  int groups, int n, int K, int G, const int* __restrict__ list,
                  const int* __restrict__ list_count, double* __restrict__ coef,
-                 double* __restrict__ dur, int* __restrict__ info) {
+                 double* __restrict__ dur, int* __restrict__ info, double* __restrict__ scratch) {
   extern __shared__ double smem[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -40,10 +66,19 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
   const int warps_per_block = blockDim.x >> 5;
   const int N = MST_NCOEF * n;
   const int R = G * K;
-  const size_t per_warp = (size_t)LD * N + (size_t)R * N + n;
-  double* AB = smem + warp * per_warp;
-  double* Bs = AB + (size_t)LD * N;  // [R][N]
-  double* Ts = Bs + (size_t)R * N;   // [n]
+  const int NS = band_rhs_stride(n);
+  double* ff = smem;   // tables shared by the CTA: ff [8][8], cf [8][LD], pi [8][LD] bytes
+  double* cf = ff + 64;
+  unsigned char* pi = reinterpret_cast<unsigned char*>(cf + MST_NCOEF * LD);
+  double* W = smem + BAND_TABLE_DOUBLES + warp * band_warp_doubles(n, R);   // window ring [WCOLS][LD]
+  double* pw = W + WCOLS * LD;                               // [n+1][8]
+  double* Bs = pw + MST_NCOEF * (n + 1);                     // [R][NS]
+  double* Ug = scratch + ((size_t)blockIdx.x * warps_per_block + warp) * UROWS * N;   // [N][UROWS]
+  for (int e = threadIdx.x; e < 64 + MST_NCOEF * LD; e += blockDim.x) band_table_entry(e, ff, cf, pi);
+  __syncthreads();
+  const BandSystem sys{n, N, pw, ff, cf, pi};
+  const bool mat_lane = lane >= 1 && lane <= KV;    // owns a column of the window
+  const int rhs0 = lane - (KV + 1);                 // first right-hand side of the lane (if >= 0)
 
   const int todo = list ? *list_count : groups;
   for (int item = blockIdx.x * warps_per_block + warp; item < todo;
@@ -51,14 +86,14 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
     const int g = list ? list[item] : item;
     const double* tg = tstamps + (size_t)g * (n + 1);
 
-    // ---- durations and input checks -------------------------------------------------
+    // ---- durations, their powers, input checks ------------------------------------------
     const double t0 = tg[0];
     int bad = 0;
     if (!(t0 >= 0.0)) bad = isfinite(t0) ? 1 : 2;
-    for (int i = lane; i < n; i += 32) {
-      const double T = tg[i + 1] - tg[i];
-      Ts[i] = T;
-      if (!(T >= 0.0) || !isfinite(T)) bad = max(bad, isfinite(T) ? 1 : 2);   // +inf counts as non-finite input
+    for (int i = lane; i <= n; i += 32) {
+      const double T = i < n ? tg[i + 1] - tg[i] : t0;
+      band_powers(T, pw + MST_NCOEF * i);
+      if (i < n && (!(T >= 0.0) || !isfinite(T))) bad = max(bad, isfinite(T) ? 1 : 2);   // +inf counts as non-finite input
     }
     bad = __reduce_max_sync(FULL, bad);
     for (int e = lane; e < G * n; e += 32)
@@ -73,40 +108,20 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
       __syncwarp();
       continue;
     }
+    __syncwarp();   // pw is complete
 
-    // ---- assemble [A | b] in shared memory ---------------------------------------------
-    for (int e = lane; e < LD * N + R * N; e += 32) AB[e] = 0.0;  // AB and Bs are contiguous
+    // ---- right-hand sides and the first kv + 1 columns ------------------------------------
+    for (int e = lane; e < R * NS; e += 32) Bs[e] = 0.0;
+    for (int e = lane; e < (KV + 1) * LD; e += 32) {
+      const int c = e / LD, o = e - c * LD;
+      W[e] = c < N ? band_entry_fast(sys, c, o) : 0.0;
+    }
     __syncwarp();
-    {
-      // first waypoint: derivatives 0..3 of piece 0 at local time t0 (quirk: t0 itself)
-      const int j = lane >> 3, k = lane & 7;
-      if (k >= j) band_set(AB, j, k, falling_factorial(k, j) * ipow(t0, k - j));
-      // last waypoint: derivatives 0..3 of piece n-1 at T_{n-1}
-      const double Tl = Ts[n - 1];
-      if (k >= j)
-        band_set(AB, N - 4 + j, MST_NCOEF * (n - 1) + k, falling_factorial(k, j) * ipow(Tl, k - j));
-    }
-    for (int e = lane; e < 64 * (n - 1); e += 32) {
-      const int i = (e >> 6) + 1;  // interior waypoint
-      const int rr = (e >> 3) & 7, k = e & 7;
-      const int s = 4 + MST_NCOEF * (i - 1);
-      const int left = MST_NCOEF * (i - 1), right = MST_NCOEF * i;
-      const double T = Ts[i - 1];
-      if (rr < 6) {  // derivative j = 1..6 continuity
-        const int j = rr + 1;
-        if (k >= j) band_set(AB, s + rr, left + k, falling_factorial(k, j) * ipow(T, k - j));
-        if (k == j) band_set(AB, s + rr, right + j, -falling_factorial(j, j));
-      } else if (rr == 6) {  // piece i-1 ends on the waypoint
-        band_set(AB, s + 6, left + k, ipow(T, k));
-      } else if (k == 0) {   // piece i starts on the waypoint
-        band_set(AB, s + 7, right, 1.0);
-      }
-    }
     for (int e = lane; e < R * (n + 1); e += 32) {
       const int r = e / (n + 1), i = e - r * (n + 1);
       const int d = r / K, k = r - d * K;
       const double v = wp[(((size_t)g * G + d) * (n + 1) + i) * K + k];
-      double* b = Bs + (size_t)r * N;
+      double* b = Bs + (size_t)r * NS;
       if (i == 0) b[0] = v;
       else if (i == n) b[N - 4] = v;
       else {
@@ -116,80 +131,88 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
     }
     __syncwarp();
 
-    // ---- banded LU with partial pivoting, right-hand sides carried along --------------
-    // Lane l owns column j + l of the active window (l <= KV) — its rows j..j+km are contiguous
-    // in the band and a stride of LD - 1 = 27 doubles apart between lanes (conflict free) — and
-    // lanes KV+1.. own one right-hand side each.  EVERY lane reads column j (broadcast loads) and
-    // repeats the pivot search and the multipliers in registers, so a step needs no reduction,
-    // no broadcast and a single warp barrier.  (First version: pivot search by shuffle
-    // reduction, swap / scale / rank-1 update as separate phases with the 150 window elements
-    // spread over the lanes: 6 barriers and ~3x the instructions per step.)
+    // ---- banded LU with partial pivoting, right-hand sides carried along --------------------
+    // Lane l in 1..kv owns column j + l of the window — its rows j..j+kl are contiguous in the band,
+    // a stride of LD - 1 = 27 doubles apart between lanes (conflict free) — and lanes kv+1.. own one
+    // right-hand side each (more than 14 of them: the extra ones in a second pass).  EVERY lane reads
+    // column j (broadcast loads) and repeats the pivot search and the multipliers in registers, so a
+    // step needs no reduction and no broadcast.  Column j itself is not updated (the multipliers are
+    // not kept: the right-hand sides move along), which leaves ONE warp barrier per step: what a step
+    // writes (columns j+1.., the right-hand sides, the slot column j-1 leaves) is disjoint from what
+    // it reads before writing (column j).  All addresses advance incrementally.
     int singular_at = 0;
+    double rinv_prev = 0.0;
+    const double* colj = W + KV;                        // column j from its diagonal down
+    const double* colj_wrap = W + WCOLS * LD + KV;
+    double* mine = mat_lane ? W + lane * LD + KV - lane : Bs + (size_t)max(rhs0, 0) * NS;   // row j of my column / rhs
+    int mine_slot = lane;
+    int live = mat_lane ? N - lane : (rhs0 >= 0 && rhs0 < R ? N : 0);   // steps this lane still takes part in
+    double* leaving = W + (WCOLS - 1) * LD + min(lane, LD - 1);          // my band position of the slot being refilled
+    int leaving_slot = WCOLS - 1;
+    double* ucol = nullptr;
     for (int j = 0; j < N; ++j) {
-      const int km = min(KL, N - 1 - j);
-      const double* colj = AB + (size_t)j * LD + KV;
-      double a[KL + 1];
-#pragma unroll
-      for (int r = 0; r <= KL; ++r) a[r] = r <= km ? colj[r] : 0.0;
-      // every lane holds column j in registers before lane 0 swaps and rewrites it below (the CUDA
-      // model does not promise lockstep between the loads above and those stores)
-      __syncwarp();
-      int jp = 0;
-      double best = fabs(a[0]);
-#pragma unroll
-      for (int r = 1; r <= KL; ++r) {
-        const double v = fabs(a[r]);
-        if (v > best) { best = v; jp = r; }  // first maximum, as LAPACK's idamax
-      }
-      if (best > 0.0) {
-        double piv = a[0];
-#pragma unroll
-        for (int r = 1; r <= KL; ++r) if (r == jp) { piv = a[r]; a[r] = a[0]; }
-        const double rinv = 1.0 / piv;
-        // my column of the window, or my right-hand side
-        double* ptr = nullptr;
-        const int c = j + lane;
-        if (lane <= KV && c < N) ptr = AB + (size_t)c * LD + KV - lane;
-        for (int q = lane - (KV + 1); q < R; q += 32 - (KV + 1)) {
-          if (q >= 0) ptr = Bs + (size_t)q * N + j;
-          if (ptr) {
-            const double x0 = ptr[0], xp = ptr[jp];
-            ptr[jp] = x0;   // row swap (a no-op when jp == 0)
-            ptr[0] = xp;
-#pragma unroll
-            for (int r = 1; r <= KL; ++r)
-              if (r <= km) ptr[r] = ptr[r] - (a[r] * rinv) * xp;
-          }
-          if (q < 0) break;  // matrix lanes have exactly one column
-        }
-        // U(j, j) must read back as the pivot (lane 0 just wrote xp = piv there) and the
-        // multipliers below it are not kept: the right-hand sides were updated in the same step
+      double l[KL + 1];
+      int jp;
+      double rinv;
+      if (band_pivot(colj, l, jp, rinv)) {
+        if (live > 0) band_update(mine, jp, l);
+        if (R > 32 - (KV + 1) && rhs0 >= 0)
+          for (int q = rhs0 + 32 - (KV + 1); q < R; q += 32 - (KV + 1)) band_update(Bs + (size_t)q * NS + j, jp, l);
       } else if (singular_at == 0) {
         singular_at = j + 1;
       }
-      __syncwarp();
-    }
-
-    // ---- back substitution with the banded upper factor -------------------------------
-    for (int j = N - 1; j >= 0; --j) {
-      const double* colj = AB + (size_t)j * LD;
-      const double ujj = colj[KV];
-      for (int r = lane; r < R; r += 32) Bs[(size_t)r * N + j] = Bs[(size_t)r * N + j] / ujj;
-      __syncwarp();
-      const int kd = min(KV, j);
-      for (int e = lane; e < kd * R; e += 32) {
-        const int rr = e / kd, d = e - rr * kd + 1;
-        Bs[(size_t)rr * N + j - d] -= colj[KV - d] * Bs[(size_t)rr * N + j];
+      band_retire(sys, leaving, ucol, j + KV + 1, lane, rinv_prev);
+      rinv_prev = rinv;
+      --live;
+      // next step: column j+1 is the pivot column, every owned column / refilled slot moves one slot on
+      colj += LD;
+      if (colj == colj_wrap) colj -= WCOLS * LD;
+      if (mat_lane) {
+        mine += LD;
+        if (++mine_slot == WCOLS) { mine_slot = 0; mine -= WCOLS * LD; }
+      } else {
+        mine += 1;
       }
+      leaving += LD;
+      if (++leaving_slot == WCOLS) { leaving_slot = 0; leaving -= WCOLS * LD; }
+      ucol = Ug + (size_t)j * UROWS + min(lane, KV);
       __syncwarp();
     }
+    if (lane <= KV) *ucol = lane == KV ? rinv_prev : *leaving;
+    __syncwarp();
 
-    // ---- coefficients out: coef[traj][piece][axis][8] -----------------------------------
-    for (int e = lane; e < R * N; e += 32) {
-      const int r = e / N, pos = e - r * N;
-      const int d = r / K, k = r - d * K;
-      const int i = pos >> 3, kk = pos & 7;
-      coef[((((size_t)g * G + d) * n + i) * K + k) * MST_NCOEF + kk] = Bs[e];
+    // ---- back substitution with the banded upper factor -------------------------------------
+    // lane d holds U(j-d, j) (d = 0: the reciprocal of the diagonal), fetched from the scratch two
+    // groups of four columns ahead of its use; lane 0 sends x_j straight to coef[traj][piece][axis][8]
+    {
+      auto fetch = [&](int j) -> double {
+        return (lane <= KV && j >= 0) ? __ldcg(Ug + (size_t)j * UROWS + KV - lane) : 0.0;
+      };
+      double nx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nx[i] = fetch(N - 1 - i);
+      double* const out0 = coef + (size_t)g * G * n * K * MST_NCOEF;
+      const int next_traj = (n - 1) * K * MST_NCOEF + MST_NCOEF;   // from the last axis of one trajectory to the first of the next
+      for (int jc = N - 1; jc >= 0; jc -= 4) {
+        double cu[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { cu[i] = nx[i]; nx[i] = fetch(jc - 4 - i); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = jc - i;   // N is a multiple of 8: never negative
+          const double rinv = __shfl_sync(FULL, cu[i], 0);
+          const int reach = min(KV, j);
+          double* bj = Bs + j;
+          double* out = out0 + (j >> 3) * K * MST_NCOEF + (j & 7);
+          for (int r = 0, k = 0; r < R; ++r) {
+            band_backsub(bj, reach, lane, cu[i], rinv, out);
+            bj += NS;
+            out += MST_NCOEF;
+            if (++k == K) { k = 0; out += next_traj - MST_NCOEF; }
+          }
+          __syncwarp();
+        }
+      }
     }
     if (lane < G) info[(size_t)g * G + lane] = singular_at;
     for (int d = 32 + lane; d < G; d += 32) info[(size_t)g * G + d] = singular_at;
@@ -197,25 +220,20 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
   }
 }
 
-// host launcher; list/list_count (device) restrict the work to listed groups when non-null
+// host launcher; list/list_count (device) restrict the work to listed groups when non-null;
+// scratch: banded_lu_scratch_bytes(groups, n, G*K) bytes of device memory
 int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K, int G,
                      const int* list, const int* list_count, double* coef, double* dur,
-                     int* info, cudaStream_t stream) {
-  const size_t per_warp = banded_lu_smem_per_warp(n, G * K);
-  int warps = (int)(MST_MAX_SMEM / per_warp);
-  if (warps < 1) return MST_ERR_TOO_LARGE;
-  if (warps > 16) warps = 16;
-  const size_t smem = per_warp * warps;
+                     int* info, double* scratch, cudaStream_t stream) {
+  const BandedPlan p = banded_plan(n, G * K);
+  if (p.warps == 0) return MST_ERR_TOO_LARGE;
+  if (!scratch) return MST_ERR_INVALID;
   {
-    const int rc = allow_dynamic_smem((const void*)banded_lu_kernel, smem);
+    const int rc = allow_dynamic_smem((const void*)banded_lu_kernel, p.smem);
     if (rc != MST_OK) return rc;
   }
-  long long blocks = ((long long)groups + warps - 1) / warps;
-  const long long cap = (long long)MST_SM_COUNT * 4;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  banded_lu_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(wp, t, groups, n, K, G, list,
-                                                                    list_count, coef, dur, info);
+  banded_lu_kernel<<<(unsigned)banded_grid(p, groups), p.warps * 32, p.smem, stream>>>(
+      wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch);
   return check_launch();
 }
 

@@ -122,7 +122,9 @@ int mst_poly_terms_at_t(const double* p, const double* t, int count, int len, do
  *   coef [B][n][K][8]  piece-major: one row of the reference's Pol_matrix per piece
  *   dur  [B][n]        durations T_i = t[i+1]-t[i]  (PiecewisePolynomial.time_durations)
  *   info [B]           MST_INFO_* per trajectory
- *   workspace          mst_solve_workspace_bytes(B, n, K, G) bytes of device scratch
+ *   workspace          mst_solve_workspace_bytes(B, n, K, G) bytes of device scratch, required by every
+ *                      solver: the list of the groups handed to the pivoted solver, and that solver's
+ *                      finished columns of U (18 x 8n doubles per resident warp, at most ~110 MB)
  */
 size_t mst_solve_workspace_bytes(int B, int n, int K, int share_time_group);
 int mst_solve_batch(const double* wp, const double* t, int B, int n, int K,

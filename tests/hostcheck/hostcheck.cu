@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <vector>
 
+#include "../../drone_path_planning_python_b200/csrc/banded_core.cuh"
 #include "../../drone_path_planning_python_b200/csrc/collide_core.cuh"
 #include "../../drone_path_planning_python_b200/csrc/condensed_core.cuh"
 #include "../../drone_path_planning_python_b200/csrc/csv_core.cuh"
@@ -95,6 +96,89 @@ extern "C" int hostcheck_format_e18(const float* v, int N, char* out, int* lengt
     char buf[32] = {0};
     lengths[i] = format_e18(v[i], buf);
     for (int j = 0; j < 32; ++j) out[32 * (size_t)i + j] = buf[j];
+  }
+  return 0;
+}
+
+// The pivoted banded solver (banded_core.cuh) with the kernel's schedule replayed on the host: every
+// phase between two warp barriers of banded_lu_kernel is a loop over the 32 lanes here.  Inputs are
+// assumed valid (finite, non-decreasing stamps).  info[g] = 0 or the first zero pivot column + 1.
+extern "C" int hostcheck_banded_lu(const double* wp, const double* t, int groups, int n, int K, int G,
+                                   double* coef, int* info) {
+  const int N = MST_NCOEF * n, R = G * K, NS = band_rhs_stride(n);
+  double ff[64], cf[MST_NCOEF * LD];
+  unsigned char pi[MST_NCOEF * LD];
+  for (int e = 0; e < 64 + MST_NCOEF * LD; ++e) band_table_entry(e, ff, cf, pi);
+  std::vector<double> W(WCOLS * LD), pw(MST_NCOEF * (n + 1)), Bs((size_t)R * NS), Ug((size_t)UROWS * N);
+  const BandSystem sys{n, N, pw.data(), ff, cf, pi};
+  for (int g = 0; g < groups; ++g) {
+    const double* tg = t + (size_t)g * (n + 1);
+    for (int i = 0; i <= n; ++i) band_powers(i < n ? tg[i + 1] - tg[i] : tg[0], pw.data() + MST_NCOEF * i);
+    std::fill(Bs.begin(), Bs.end(), 0.0);
+    std::fill(W.begin(), W.end(), -77.0);   // the last slot is garbage until a column is assembled into it
+    std::fill(Ug.begin(), Ug.end(), -99.0);
+    for (int e = 0; e < (KV + 1) * LD; ++e) {
+      const int c = e / LD, o = e - c * LD;
+      W[e] = c < N ? band_entry_fast(sys, c, o) : 0.0;
+      if (c < N && band_entry_fast(sys, c, o) != band_entry(sys, c, o)) return -2;
+    }
+    for (int r = 0; r < R; ++r) {
+      const int d = r / K, k = r - d * K;
+      double* b = Bs.data() + (size_t)r * NS;
+      for (int i = 0; i <= n; ++i) {
+        const double v = wp[(((size_t)g * G + d) * (n + 1) + i) * K + k];
+        if (i == 0) b[0] = v;
+        else if (i == n) b[N - 4] = v;
+        else b[4 + MST_NCOEF * (i - 1) + 6] = b[4 + MST_NCOEF * (i - 1) + 7] = v;
+      }
+    }
+    int singular_at = 0, jm = 0, sprev = WCOLS - 1;
+    double rinv_prev = 0.0;
+    for (int j = 0; j < N; ++j) {
+      double l[KL + 1];
+      int jp;
+      double rinv;
+      const bool ok = band_pivot(W.data() + jm * LD + KV, l, jp, rinv);
+      if (!ok && singular_at == 0) singular_at = j + 1;
+      for (int lane = 0; lane < 32; ++lane) {
+        if (ok) {
+          double* ptr = nullptr;
+          if (lane >= 1 && lane <= KV && j + lane < N) {
+            int sl = jm + lane;
+            if (sl >= WCOLS) sl -= WCOLS;
+            ptr = W.data() + sl * LD + KV - lane;
+          }
+          for (int q = lane - (KV + 1); q < R; q += 32 - (KV + 1)) {
+            if (q >= 0) ptr = Bs.data() + (size_t)q * NS + j;
+            if (ptr) band_update(ptr, jp, l);
+            if (q < 0) break;
+          }
+        }
+        if (lane < LD && j + KV + 1 < N && band_entry_fast(sys, j + KV + 1, lane) != band_entry(sys, j + KV + 1, lane))
+          return -2;   // the pattern tables must reproduce the rules they were derived from
+        band_retire(sys, W.data() + sprev * LD + (lane < LD ? lane : LD - 1),
+                    j > 0 ? Ug.data() + (size_t)(j - 1) * UROWS + (lane < KV ? lane : KV) : nullptr, j + KV + 1, lane,
+                    rinv_prev);
+      }
+      rinv_prev = rinv;
+      sprev = jm;
+      jm = jm + 1 == WCOLS ? 0 : jm + 1;
+    }
+    for (int lane = 0; lane <= KV; ++lane)
+      Ug[(size_t)(N - 1) * UROWS + lane] = lane == KV ? rinv_prev : W[sprev * LD + lane];
+    for (int j = N - 1; j >= 0; --j) {
+      const double rinv = Ug[(size_t)j * UROWS + KV];
+      for (int r = 0; r < R; ++r) {
+        const int d = r / K, k = r - d * K;
+        // lanes in DESCENDING order: a lane must not see what a lower lane wrote in this phase
+        for (int lane = 31; lane >= 0; --lane) {
+          const double u = lane <= KV ? Ug[(size_t)j * UROWS + KV - lane] : 0.0;
+          band_backsub(Bs.data() + (size_t)r * NS + j, j < KV ? j : KV, lane, u, rinv,
+                       coef + ((((size_t)g * G + d) * n + (j >> 3)) * K + k) * MST_NCOEF + (j & 7));
+        }
+      }
+    }
+    for (int d = 0; d < G; ++d) info[(size_t)g * G + d] = singular_at;
   }
   return 0;
 }

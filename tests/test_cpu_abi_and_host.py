@@ -363,3 +363,62 @@ def test_culled_routine_on_a_large_morton_ordered_environment():
     assert rc >= 0
     ref = build_oracle.c_collide_poses(robot, env, poses)
     assert np.array_equal(out, ref) and 0.1 < ref.mean() < 0.9
+
+
+@pytest.mark.parametrize("n,K,G", [(1, 3, 1), (2, 4, 1), (3, 3, 2), (10, 3, 1), (10, 4, 5), (20, 3, 1), (49, 3, 1)])
+def test_banded_window_lu_matches_oracle(n, K, G):
+    """The pivoted solver's arithmetic and storage scheme (banded_core.cuh: window ring, finished columns
+    of U in a scratch, columns recomputed on entry) with the kernel's warp schedule replayed lane by lane:
+    normwise 1e-9 against the dense pivoted solve for duration spreads up to 100:1 and the t[0] != 0 quirk,
+    and a relative residual of the reference's own equations at rounding level (backward stability does
+    not depend on the conditioning, the 1e-9 does)."""
+    from oracle import minsnap_oracle as mo
+    lib = _hostcheck()
+    rng = np.random.default_rng(100 * n + 10 * K + G)
+    # (t[0] = 0.7 sits inside the range of the first duration: the quirk's matrix is singular when they are
+    # equal, LAPACK's own banded and dense solves differ by up to 1e-6 there; only the residual is asserted)
+    for spread, t0, tol in ((1.0, 0.0, 1e-9), (4.0, 0.0, 1e-9), (100.0, 0.0, 1e-9), (4.0, 0.1, 1e-9), (30.0, 0.7, None)):
+        groups = 4
+        B = groups * G
+        T = 0.3 * np.exp(rng.uniform(0, np.log(max(spread, 1.0001)), (groups, n)))
+        T[:, rng.integers(n)] = 0.3
+        t = np.concatenate([np.full((groups, 1), t0), t0 + np.cumsum(T, axis=1)], axis=1)
+        wp = np.cumsum(rng.normal(0, 0.5, (B, n + 1, K)), axis=1)
+        coef = np.full((B, n, K, 8), np.nan)
+        info = np.full(B, -5, dtype=np.int32)
+        assert lib.hostcheck_banded_lu(P(wp.ctypes.data), P(t.ctypes.data), groups, n, K, G, P(coef.ctypes.data),
+                                       P(info.ctypes.data)) == 0
+        assert (info == 0).all()
+        for b in range(B):
+            ref, _ = mo.solve_waypoints(wp[b], t[b // G])
+            err = (np.abs(coef[b] - ref).max(axis=(0, 2)) / np.abs(ref).max(axis=(0, 2))).max()
+            assert tol is None or err <= tol, (spread, t0, b, err)
+            for k in range(K):
+                A, rhs, _ = mo.assemble_system(wp[b][:, k], t[b // G])
+                x = coef[b][:, k, :].reshape(-1, 1)
+                row_scale = np.abs(A) @ np.abs(x) + np.abs(rhs)
+                assert (np.abs(A @ x - rhs) <= 1e-13 * np.maximum(row_scale, row_scale.max() * 1e-16)).all() or \
+                    np.abs(A @ x - rhs).max() <= 1e-12 * row_scale.max()
+
+
+def test_banded_window_lu_reports_the_zero_pivot():
+    """A zero-length piece makes the reference's matrix singular (np.linalg.solve raises): info = the
+    1-based column of the first zero pivot, as LAPACK's dgbsv would return it."""
+    import scipy.linalg as sl
+    from oracle import minsnap_oracle as mo
+    lib = _hostcheck()
+    n, K = 6, 3
+    t = np.array([[0, 1, 1, 3, 4, 5, 6.0]])
+    wp = np.arange((n + 1) * K, dtype=np.float64).reshape(1, n + 1, K)
+    coef = np.zeros((1, n, K, 8))
+    info = np.zeros(1, dtype=np.int32)
+    lib.hostcheck_banded_lu(P(wp.ctypes.data), P(t.ctypes.data), 1, n, K, 1, P(coef.ctypes.data), P(info.ctypes.data))
+    A, rhs, _ = mo.assemble_system(wp[0][:, 0], t[0])
+    N = 8 * n
+    ab = np.zeros((28, N))
+    for i in range(N):
+        for j in range(max(0, i - 10), min(N, i + 8)):
+            ab[17 + i - j, j] = A[i, j]
+    gbsv, = sl.get_lapack_funcs(("gbsv",), (ab,))
+    _, _, _, lapack_info = gbsv(10, 7, ab, rhs.copy())
+    assert lapack_info > 0 and int(info[0]) == lapack_info
