@@ -110,14 +110,30 @@ __host__ __device__ __forceinline__ double band_entry_fast(const BandSystem& s, 
 // the multipliers l_r = a_r / pivot formed as dgbtf2 does (reciprocal, then scale) — for the rows in
 // their places BEFORE the swap: band_update puts the one row the swap moves right.  Returns false for
 // a zero (or NaN) pivot column; rinv is then 1 / U(j,j), what a division by that diagonal multiplies with.
+// one node of the pivot tournament: the left candidate (lower rows) stays unless the right one is strictly
+// larger in magnitude — the first maximum wins, as in idamax
+__host__ __device__ __forceinline__ void band_pick(double& v, int& i, double w, int iw) {
+  if (fabs(w) > fabs(v)) { v = w; i = iw; }
+}
+
 __host__ __device__ __forceinline__ bool band_pivot(const double* colj, double (&l)[KL + 1], int& jp, double& rinv) {
 #pragma unroll
   for (int r = 0; r <= KL; ++r) l[r] = colj[r];
-  jp = 0;
-  double piv = l[0];
-#pragma unroll
-  for (int r = 1; r <= KL; ++r)
-    if (fabs(l[r]) > fabs(piv)) { piv = l[r]; jp = r; }
+  // 10 comparisons as a tree of depth 4 instead of a chain of 10 (the step's critical path)
+  double v0 = l[0], v2 = l[2], v4 = l[4], v6 = l[6], v8 = l[8];
+  int i0 = 0, i2 = 2, i4 = 4, i6 = 6, i8 = 8;
+  band_pick(v0, i0, l[1], 1);
+  band_pick(v2, i2, l[3], 3);
+  band_pick(v4, i4, l[5], 5);
+  band_pick(v6, i6, l[7], 7);
+  band_pick(v8, i8, l[9], 9);
+  band_pick(v0, i0, v2, i2);
+  band_pick(v4, i4, v6, i6);
+  band_pick(v8, i8, l[10], 10);
+  band_pick(v0, i0, v4, i4);
+  band_pick(v0, i0, v8, i8);
+  const double piv = v0;
+  jp = i0;
   rinv = 1.0 / piv;
   if (!(fabs(piv) > 0.0)) return false;
 #pragma unroll
@@ -151,14 +167,14 @@ __host__ __device__ __forceinline__ void band_retire(const BandSystem& s, double
 }
 
 // Back substitution, column j, one right-hand side b, lane d: every lane forms x_j = b_j / U(j,j)
-// itself (rinv = the stored reciprocal), lane 0 sends it to its final place, lane d in 1..kv removes
+// itself (rinv = the stored reciprocal), one lane sends it to its final place, lane d in 1..kv removes
 // U(j-d, j) x_j from b[j-d].
-// (bj points at b[j]; reach = min(kv, j).)
-__host__ __device__ __forceinline__ void band_backsub(double* bj, int reach, int lane, double u, double rinv,
-                                                      double* out) {
+// (bj points at b[j]; reach = min(kv, j); lane `writer` is the one that stores x_j, through ITS out.)
+__host__ __device__ __forceinline__ void band_backsub(double* bj, int reach, int lane, int writer, double u,
+                                                      double rinv, double* out) {
   const double x = bj[0] * rinv;
-  if (lane == 0) *out = x;
-  else if (lane <= reach) bj[-lane] -= u * x;
+  if (lane == writer) *out = x;
+  if (lane >= 1 && lane <= reach) bj[-lane] -= u * x;
 }
 
 // right-hand sides in shared memory: 8n entries and kl + 1 of slack for the unguarded updates of the last

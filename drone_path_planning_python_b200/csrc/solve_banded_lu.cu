@@ -156,8 +156,8 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
       double rinv;
       if (band_pivot(colj, l, jp, rinv)) {
         if (live > 0) band_update(mine, jp, l);
-        if (R > 32 - (KV + 1) && rhs0 >= 0)
-          for (int q = rhs0 + 32 - (KV + 1); q < R; q += 32 - (KV + 1)) band_update(Bs + (size_t)q * NS + j, jp, l);
+        if (rhs0 >= 0)   // more right-hand sides than lanes: the same row of every 14th one behind mine
+          for (int m = 32 - (KV + 1); rhs0 + m < R; m += 32 - (KV + 1)) band_update(mine + (size_t)m * NS, jp, l);
       } else if (singular_at == 0) {
         singular_at = j + 1;
       }
@@ -191,8 +191,11 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
       double nx[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) nx[i] = fetch(N - 1 - i);
+      // right-hand side r = d K + k is axis k of trajectory d of the group; lane r (mod 32) keeps where its
+      // coefficients go and stores x_j itself
       double* const out0 = coef + (size_t)g * G * n * K * MST_NCOEF;
       const int next_traj = (n - 1) * K * MST_NCOEF + MST_NCOEF;   // from the last axis of one trajectory to the first of the next
+      double* myout = out0 + ((size_t)(lane / K) * n * K + lane % K) * MST_NCOEF;
       for (int jc = N - 1; jc >= 0; jc -= 4) {
         double cu[4];
 #pragma unroll
@@ -203,12 +206,20 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
           const double rinv = __shfl_sync(FULL, cu[i], 0);
           const int reach = min(KV, j);
           double* bj = Bs + j;
-          double* out = out0 + (j >> 3) * K * MST_NCOEF + (j & 7);
-          for (int r = 0, k = 0; r < R; ++r) {
-            band_backsub(bj, reach, lane, cu[i], rinv, out);
-            bj += NS;
-            out += MST_NCOEF;
-            if (++k == K) { k = 0; out += next_traj - MST_NCOEF; }
+          const int colofs = (j >> 3) * K * MST_NCOEF + (j & 7);
+          if (R <= 32) {
+            for (int r = 0; r < R; ++r) {
+              band_backsub(bj, reach, lane, r, cu[i], rinv, myout + colofs);
+              bj += NS;
+            }
+          } else {
+            double* out = out0 + colofs;
+            for (int r = 0, k = 0; r < R; ++r) {
+              band_backsub(bj, reach, lane, 0, cu[i], rinv, out);
+              bj += NS;
+              out += MST_NCOEF;
+              if (++k == K) { k = 0; out += next_traj - MST_NCOEF; }
+            }
           }
           __syncwarp();
         }

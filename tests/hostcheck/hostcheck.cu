@@ -173,7 +173,7 @@ extern "C" int hostcheck_banded_lu(const double* wp, const double* t, int groups
         // lanes in DESCENDING order: a lane must not see what a lower lane wrote in this phase
         for (int lane = 31; lane >= 0; --lane) {
           const double u = lane <= KV ? Ug[(size_t)j * UROWS + KV - lane] : 0.0;
-          band_backsub(Bs.data() + (size_t)r * NS + j, j < KV ? j : KV, lane, u, rinv,
+          band_backsub(Bs.data() + (size_t)r * NS + j, j < KV ? j : KV, lane, r % 32, u, rinv,
                        coef + ((((size_t)g * G + d) * n + (j >> 3)) * K + k) * MST_NCOEF + (j & 7));
         }
       }
