@@ -7,13 +7,16 @@
 // it after fill-in, element (row, col) at band position o = kv + row - col of its column.  Only a
 // WINDOW of the band lives in shared memory: at elimination step j the columns j .. j+kv are being
 // updated, column j-1 has just become a finished column of U and the columns from j+kv+1 on have not
-// been touched yet.  So the window is a ring of kv + 2 column slots; a finished column goes out to a
+// been touched yet.  So the window is a ring of kv + 3 column slots; a finished column goes out to a
 // per-warp scratch in device memory (18 doubles, read back once by the back substitution — the
 // scratch of all resident warps is ~50-100 MB, i.e. L2-resident), and the slot it leaves is refilled
 // with the next untouched column, whose entries are recomputed from the table of duration powers
 // (band_entry) instead of being stored.  Shared memory per warp drops from 28 x 8n doubles to
-// 19 x 28, i.e. from 5 resident warps per SM at n = 20 to 24.
+// 20 x 28, i.e. from 5 resident warps per SM at n = 20 to 20.  What bounds the kernel is the shared-memory
+// data pipe (90 % of its wavefronts busy, profiles/): the layout rules below are about wavefronts.
 #pragma once
+#include <string.h>
+
 #include "mst_common.cuh"
 
 namespace mst {
@@ -22,7 +25,14 @@ constexpr int KL = 10;
 constexpr int KU = 7;
 constexpr int KV = KL + KU;          // upper bandwidth after fill-in
 constexpr int LD = 2 * KL + KU + 1;  // 28 band positions per column
-constexpr int WCOLS = KV + 2;        // column slots of the window ring
+constexpr int WCOLS = KV + 3;        // column slots of the window ring: kv + 1 in use, one being refilled, and one
+                                     // more so that WCOLS * LD is a multiple of 16 doubles — a column keeps its
+                                     // shared-memory banks when the ring wraps
+constexpr int MAT_LANES = KV;        // lane l < MAT_LANES owns column j + 1 + l of the window: lanes 0..15 (one
+                                     // half-warp = one 128-byte wavefront per 64-bit access) are 27 doubles apart,
+                                     // 16 different bank pairs; column j + kv and the right-hand sides share the
+                                     // other half-warp
+constexpr int RHS_LANES = 32 - MAT_LANES;
 constexpr int UROWS = KV + 1;        // doubles per finished column of U (rows col-kv .. col)
 
 struct BandSystem {
@@ -116,24 +126,53 @@ __host__ __device__ __forceinline__ void band_pick(double& v, int& i, double w, 
   if (fabs(w) > fabs(v)) { v = w; i = iw; }
 }
 
-__host__ __device__ __forceinline__ bool band_pivot(const double* colj, double (&l)[KL + 1], int& jp, double& rinv) {
+// magnitude of a double as an integer key: |x| < |y|  <=>  key(x) < key(y) for everything but NaN
+__host__ __device__ __forceinline__ unsigned long long band_key(double x) {
+  unsigned long long u;
+  memcpy(&u, &x, sizeof(u));
+  return u & 0x7fffffffffffffffull;
+}
+
+// The pivot of step j: the first row of largest magnitude, as idamax picks it.  Two searches:
+//   WARP = false  every lane runs the 10 comparisons itself, as a tree of depth 4 instead of a chain of 10
+//                 (the search is on the step's critical path);
+//   WARP = true   (device only; all 32 lanes must call) lane r offers row r and two integer warp reductions
+//                 — high word of the magnitude bits, then low word among the lanes holding the largest high
+//                 word — find the largest; the lowest such lane wins.  50 instructions fewer per step.
+template <bool WARP>
+__host__ __device__ __forceinline__ bool band_pivot(const double* colj, int lane, double (&l)[KL + 1], int& jp,
+                                                    double& rinv) {
 #pragma unroll
   for (int r = 0; r <= KL; ++r) l[r] = colj[r];
-  // 10 comparisons as a tree of depth 4 instead of a chain of 10 (the step's critical path)
-  double v0 = l[0], v2 = l[2], v4 = l[4], v6 = l[6], v8 = l[8];
-  int i0 = 0, i2 = 2, i4 = 4, i6 = 6, i8 = 8;
-  band_pick(v0, i0, l[1], 1);
-  band_pick(v2, i2, l[3], 3);
-  band_pick(v4, i4, l[5], 5);
-  band_pick(v6, i6, l[7], 7);
-  band_pick(v8, i8, l[9], 9);
-  band_pick(v0, i0, v2, i2);
-  band_pick(v4, i4, v6, i6);
-  band_pick(v8, i8, l[10], 10);
-  band_pick(v0, i0, v4, i4);
-  band_pick(v0, i0, v8, i8);
-  const double piv = v0;
-  jp = i0;
+  double piv;
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 800
+  if (WARP) {
+    const double own = lane <= KL ? colj[lane] : 0.0;
+    const unsigned hi = (unsigned)__double2hiint(own) & 0x7fffffffu;
+    const unsigned top_hi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo = hi == top_hi ? (unsigned)__double2loint(own) : 0u;
+    const unsigned top_lo = __reduce_max_sync(0xffffffffu, lo);
+    jp = __ffs(__ballot_sync(0xffffffffu, hi == top_hi && lo == top_lo)) - 1;
+    piv = __shfl_sync(0xffffffffu, own, jp);
+  } else
+#endif
+  {
+    (void)lane;
+    double v0 = l[0], v2 = l[2], v4 = l[4], v6 = l[6], v8 = l[8];
+    int i0 = 0, i2 = 2, i4 = 4, i6 = 6, i8 = 8;
+    band_pick(v0, i0, l[1], 1);
+    band_pick(v2, i2, l[3], 3);
+    band_pick(v4, i4, l[5], 5);
+    band_pick(v6, i6, l[7], 7);
+    band_pick(v8, i8, l[9], 9);
+    band_pick(v0, i0, v2, i2);
+    band_pick(v4, i4, v6, i6);
+    band_pick(v8, i8, l[10], 10);
+    band_pick(v0, i0, v4, i4);
+    band_pick(v0, i0, v8, i8);
+    piv = v0;
+    jp = i0;
+  }
   rinv = 1.0 / piv;
   if (!(fabs(piv) > 0.0)) return false;
 #pragma unroll
@@ -158,23 +197,36 @@ __host__ __device__ __forceinline__ void band_update(double* ptr, int jp, const 
 // j = 0; its diagonal is kept as the reciprocal the back substitution multiplies with) and column
 // newcol = j + kv + 1 takes the slot.  Lane l reads band position l and then writes band position l:
 // no other lane touches this slot during the step.
-// (slot and ucol already point at this lane's band position.)
-__host__ __device__ __forceinline__ void band_retire(const BandSystem& s, double* slot, double* ucol, int newcol,
-                                                     int lane, double rinv_prev) {
+// (slot and ucol already point at this lane's band position; first: j == 0, nothing leaves yet.)  In two
+// halves so that the kernel can issue the loads at the top of the step and the stores at its end.
+__host__ __device__ __forceinline__ void band_retire_fetch(const BandSystem& s, const double* slot, int newcol,
+                                                           int lane, double* leaves, double* enters) {
+  *leaves = 0.0;
+  *enters = 0.0;
   if (lane >= LD) return;
-  if (ucol != nullptr && lane <= KV) *ucol = lane == KV ? rinv_prev : *slot;
-  if (newcol < s.N) *slot = band_entry_fast(s, newcol, lane);
+  *leaves = *slot;
+  if (newcol < s.N) *enters = band_entry_fast(s, newcol, lane);
+}
+
+// (slot: this lane's band position of the slot column newcol goes to — the one column j-2 left a step ago.)
+__host__ __device__ __forceinline__ void band_retire_store(const BandSystem& s, double* slot, double* ucol,
+                                                           bool first, int newcol, int lane, double rinv_prev,
+                                                           double leaves, double enters) {
+  if (lane >= LD) return;
+  if (!first && lane <= KV) *ucol = lane == KV ? rinv_prev : leaves;
+  if (newcol < s.N) *slot = enters;
 }
 
 // Back substitution, column j, one right-hand side b, lane d: every lane forms x_j = b_j / U(j,j)
 // itself (rinv = the stored reciprocal), one lane sends it to its final place, lane d in 1..kv removes
 // U(j-d, j) x_j from b[j-d].
-// (bj points at b[j]; reach = min(kv, j); lane `writer` is the one that stores x_j, through ITS out.)
-__host__ __device__ __forceinline__ void band_backsub(double* bj, int reach, int lane, int writer, double u,
+// (bj points at b[j]; this lane holds u = U(j-d, j), d = 0 meaning none; lane `writer` is the one that stores
+// x_j, through ITS out.  A zero u — the fill-in never reached that far — costs no shared-memory access.)
+__host__ __device__ __forceinline__ void band_backsub(double* bj, int d, int lane, int writer, double u,
                                                       double rinv, double* out) {
   const double x = bj[0] * rinv;
   if (lane == writer) *out = x;
-  if (lane >= 1 && lane <= reach) bj[-lane] -= u * x;
+  if (d > 0 && u != 0.0) bj[-d] -= u * x;
 }
 
 // right-hand sides in shared memory: 8n entries and kl + 1 of slack for the unguarded updates of the last

@@ -9,6 +9,8 @@
 // all: banded_core.cuh holds the arithmetic and the storage scheme (window ring in shared memory,
 // finished columns of U in an L2-resident per-warp scratch, untouched columns recomputed from the
 // durations when they enter the window).
+#include <stdlib.h>
+
 #include "banded_core.cuh"
 
 namespace mst {
@@ -16,6 +18,7 @@ namespace mst {
 constexpr int BANDED_WARPS = 4;        // warps (time groups in flight) per CTA
 constexpr int BANDED_MIN_CTAS = 6;     // resident CTAs the register bound keeps possible (80 registers)
 constexpr int BANDED_WARPS_PER_SM = BANDED_WARPS * BANDED_MIN_CTAS;
+constexpr int BANDED_VARIANT = 1;      // see banded_lu_kernel (MST_LU_VARIANT overrides, for A/B measurements)
 
 __host__ size_t banded_lu_smem_per_warp(int n, int R) { return sizeof(double) * band_warp_doubles(n, R); }
 
@@ -54,6 +57,8 @@ __host__ size_t banded_lu_scratch_bytes(int groups, int n, int R) {
   return sizeof(double) * (size_t)banded_grid(p, groups) * p.warps * UROWS * MST_NCOEF * n;
 }
 
+// V: bit 0 = warp-wide pivot search, bit 1 = the refill's loads issued at the top of the step
+template <int V>
 __global__ void __launch_bounds__(BANDED_WARPS * 32, BANDED_MIN_CTAS)
 banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps,
                  int groups, int n, int K, int G, const int* __restrict__ list,
@@ -77,8 +82,8 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
   for (int e = threadIdx.x; e < 64 + MST_NCOEF * LD; e += blockDim.x) band_table_entry(e, ff, cf, pi);
   __syncthreads();
   const BandSystem sys{n, N, pw, ff, cf, pi};
-  const bool mat_lane = lane >= 1 && lane <= KV;    // owns a column of the window
-  const int rhs0 = lane - (KV + 1);                 // first right-hand side of the lane (if >= 0)
+  const bool mat_lane = lane < MAT_LANES;           // owns column j + 1 + lane of the window
+  const int rhs0 = lane - MAT_LANES;                // first right-hand side of the lane (if >= 0)
 
   const int todo = list ? *list_count : groups;
   for (int item = blockIdx.x * warps_per_block + warp; item < todo;
@@ -132,61 +137,74 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
     __syncwarp();
 
     // ---- banded LU with partial pivoting, right-hand sides carried along --------------------
-    // Lane l in 1..kv owns column j + l of the window — its rows j..j+kl are contiguous in the band,
-    // a stride of LD - 1 = 27 doubles apart between lanes (conflict free) — and lanes kv+1.. own one
-    // right-hand side each (more than 14 of them: the extra ones in a second pass).  EVERY lane reads
-    // column j (broadcast loads) and repeats the pivot search and the multipliers in registers, so a
-    // step needs no reduction and no broadcast.  Column j itself is not updated (the multipliers are
-    // not kept: the right-hand sides move along), which leaves ONE warp barrier per step: what a step
-    // writes (columns j+1.., the right-hand sides, the slot column j-1 leaves) is disjoint from what
-    // it reads before writing (column j).  All addresses advance incrementally.
+    // Lane l < kv owns column j + 1 + l of the window — its rows j..j+kl are contiguous in the band,
+    // a stride of LD - 1 = 27 doubles apart between lanes (16 lanes = 16 bank pairs: one wavefront) — and
+    // the lanes from kv on own one right-hand side each (more than 15 of them: the extra ones in further
+    // passes).  EVERY lane reads column j (broadcast loads) and repeats the pivot search and the
+    // multipliers in registers, so a step needs no reduction and no broadcast.  Column j itself is not
+    // updated (the multipliers are not kept: the right-hand sides move along), which leaves ONE warp
+    // barrier per step: what a step writes (columns j+1.., the right-hand sides, the slot column j-2 left)
+    // is disjoint from what it reads before writing (column j, column j-1 on its way out).
     int singular_at = 0;
     double rinv_prev = 0.0;
-    const double* colj = W + KV;                        // column j from its diagonal down
-    const double* colj_wrap = W + WCOLS * LD + KV;
-    double* mine = mat_lane ? W + lane * LD + KV - lane : Bs + (size_t)max(rhs0, 0) * NS;   // row j of my column / rhs
-    int mine_slot = lane;
-    int live = mat_lane ? N - lane : (rhs0 >= 0 && rhs0 < R ? N : 0);   // steps this lane still takes part in
-    double* leaving = W + (WCOLS - 1) * LD + min(lane, LD - 1);          // my band position of the slot being refilled
-    int leaving_slot = WCOLS - 1;
-    double* ucol = nullptr;
+    // three walking pointers, each one column slot further every step and back to the first slot after the
+    // last (a countdown instead of a comparison against a pointer the compiler would recompute every step):
+    //   colj    column j from its diagonal down;
+    //   mine    row j of my column of the window (matrix lanes) / of my right-hand side (those just move one
+    //           row down and never wrap);
+    //   leaving my band position of the slot that is being refilled (column j-1 goes, j+kv+1 comes).
+    // (element offsets from the start of the dynamic shared memory, made opaque to the compiler: carried in a
+    // register instead of being re-derived from the kernel parameters every step, and still shared-memory
+    // accesses — an opaque POINTER turns them into generic loads.)
+    int colj = (int)(W - smem) + KV;
+    int colj_left = WCOLS;
+    int mine = (int)((mat_lane ? W + (lane + 1) * LD + KV - (lane + 1) : Bs + (size_t)rhs0 * NS) - smem);
+    const int mine_step = mat_lane ? LD : 1;
+    int mine_left = mat_lane ? WCOLS - (lane + 1) : 0x7fffffff;
+    int live = mat_lane ? N - (lane + 1) : (rhs0 < R ? N : 0);   // steps this lane still takes part in
+    int leaving = (int)(W - smem) + (WCOLS - 1) * LD + min(lane, LD - 1);    // column j-1 (none yet)
+    int leaving_left = 1;
+    int entering = leaving - LD;                                            // where column j+kv+1 goes
+    int entering_left = 2;
+    double* ucol = Ug + min(lane, KV) - UROWS;                          // column j-1 of the scratch
+    asm volatile("" : "+r"(colj), "+r"(mine), "+r"(leaving), "+r"(entering));
     for (int j = 0; j < N; ++j) {
       double l[KL + 1];
       int jp;
-      double rinv;
-      if (band_pivot(colj, l, jp, rinv)) {
-        if (live > 0) band_update(mine, jp, l);
-        if (rhs0 >= 0)   // more right-hand sides than lanes: the same row of every 14th one behind mine
-          for (int m = 32 - (KV + 1); rhs0 + m < R; m += 32 - (KV + 1)) band_update(mine + (size_t)m * NS, jp, l);
+      double rinv, leaves = 0.0, enters = 0.0;
+      if (V & 2) band_retire_fetch(sys, smem + leaving, j + KV + 1, lane, &leaves, &enters);   // loads off the critical path
+      if (band_pivot<(V & 1) != 0>(smem + colj, lane, l, jp, rinv)) {
+        if (live > 0) band_update(smem + mine, jp, l);
+        if (rhs0 >= 0)   // more right-hand sides than lanes: the same row of every 15th one behind mine
+          for (int m = RHS_LANES; rhs0 + m < R; m += RHS_LANES) band_update(smem + mine + (size_t)m * NS, jp, l);
       } else if (singular_at == 0) {
         singular_at = j + 1;
       }
-      band_retire(sys, leaving, ucol, j + KV + 1, lane, rinv_prev);
+      if (!(V & 2)) band_retire_fetch(sys, smem + leaving, j + KV + 1, lane, &leaves, &enters);
+      band_retire_store(sys, smem + entering, ucol, j == 0, j + KV + 1, lane, rinv_prev, leaves, enters);
       rinv_prev = rinv;
       --live;
-      // next step: column j+1 is the pivot column, every owned column / refilled slot moves one slot on
       colj += LD;
-      if (colj == colj_wrap) colj -= WCOLS * LD;
-      if (mat_lane) {
-        mine += LD;
-        if (++mine_slot == WCOLS) { mine_slot = 0; mine -= WCOLS * LD; }
-      } else {
-        mine += 1;
-      }
+      if (--colj_left == 0) { colj_left = WCOLS; colj -= WCOLS * LD; }
+      mine += mine_step;
+      if (--mine_left == 0) { mine_left = WCOLS; mine -= WCOLS * LD; }
       leaving += LD;
-      if (++leaving_slot == WCOLS) { leaving_slot = 0; leaving -= WCOLS * LD; }
-      ucol = Ug + (size_t)j * UROWS + min(lane, KV);
+      if (--leaving_left == 0) { leaving_left = WCOLS; leaving -= WCOLS * LD; }
+      entering += LD;
+      if (--entering_left == 0) { entering_left = WCOLS; entering -= WCOLS * LD; }
+      ucol += UROWS;
       __syncwarp();
     }
-    if (lane <= KV) *ucol = lane == KV ? rinv_prev : *leaving;
+    if (lane <= KV) *ucol = lane == KV ? rinv_prev : smem[leaving];
     __syncwarp();
 
     // ---- back substitution with the banded upper factor -------------------------------------
-    // lane d holds U(j-d, j) (d = 0: the reciprocal of the diagonal), fetched from the scratch two
-    // groups of four columns ahead of its use; lane 0 sends x_j straight to coef[traj][piece][axis][8]
+    // lane d-1 holds U(j-d, j) for d = 1..kv (the first 16 of them: one half-warp), lane kv the reciprocal of
+    // the diagonal; fetched from the scratch two groups of four columns ahead of their use.  x_j goes
+    // straight to coef[traj][piece][axis][8].
     {
       auto fetch = [&](int j) -> double {
-        return (lane <= KV && j >= 0) ? __ldcg(Ug + (size_t)j * UROWS + KV - lane) : 0.0;
+        return (lane <= KV && j >= 0) ? __ldcg(Ug + (size_t)j * UROWS + (lane < KV ? KV - 1 - lane : KV)) : 0.0;
       };
       double nx[4];
 #pragma unroll
@@ -203,19 +221,33 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int j = jc - i;   // N is a multiple of 8: never negative
-          const double rinv = __shfl_sync(FULL, cu[i], 0);
-          const int reach = min(KV, j);
+          const double rinv = __shfl_sync(FULL, cu[i], KV);
+          const int d = (lane < KV && lane < j) ? lane + 1 : 0;   // my row of U exists
           double* bj = Bs + j;
           const int colofs = (j >> 3) * K * MST_NCOEF + (j & 7);
           if (R <= 32) {
-            for (int r = 0; r < R; ++r) {
-              band_backsub(bj, reach, lane, r, cu[i], rinv, myout + colofs);
+            int r = 0;
+            for (; r + 3 <= R; r += 3) {   // three independent right-hand sides in flight (the axes of one drone)
+              const double x0 = bj[0] * rinv, x1 = bj[NS] * rinv, x2 = bj[2 * NS] * rinv;
+              if (lane == r) myout[colofs] = x0;
+              if (lane == r + 1) myout[colofs] = x1;
+              if (lane == r + 2) myout[colofs] = x2;
+              if (d > 0 && cu[i] != 0.0) {
+                const double b0 = bj[-d], b1 = bj[NS - d], b2 = bj[2 * NS - d];
+                bj[-d] = b0 - cu[i] * x0;
+                bj[NS - d] = b1 - cu[i] * x1;
+                bj[2 * NS - d] = b2 - cu[i] * x2;
+              }
+              bj += 3 * NS;
+            }
+            for (; r < R; ++r) {
+              band_backsub(bj, d, lane, r, cu[i], rinv, myout + colofs);
               bj += NS;
             }
           } else {
             double* out = out0 + colofs;
             for (int r = 0, k = 0; r < R; ++r) {
-              band_backsub(bj, reach, lane, 0, cu[i], rinv, out);
+              band_backsub(bj, d, lane, 0, cu[i], rinv, out);
               bj += NS;
               out += MST_NCOEF;
               if (++k == K) { k = 0; out += next_traj - MST_NCOEF; }
@@ -239,12 +271,20 @@ int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K
   const BandedPlan p = banded_plan(n, G * K);
   if (p.warps == 0) return MST_ERR_TOO_LARGE;
   if (!scratch) return MST_ERR_INVALID;
+  static const int variant = getenv("MST_LU_VARIANT") ? atoi(getenv("MST_LU_VARIANT")) & 3 : BANDED_VARIANT;
+  const void* kernels[4] = {(const void*)banded_lu_kernel<0>, (const void*)banded_lu_kernel<1>,
+                            (const void*)banded_lu_kernel<2>, (const void*)banded_lu_kernel<3>};
   {
-    const int rc = allow_dynamic_smem((const void*)banded_lu_kernel, p.smem);
+    const int rc = allow_dynamic_smem(kernels[variant], p.smem);
     if (rc != MST_OK) return rc;
   }
-  banded_lu_kernel<<<(unsigned)banded_grid(p, groups), p.warps * 32, p.smem, stream>>>(
-      wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch);
+  const unsigned grid = (unsigned)banded_grid(p, groups);
+  switch (variant) {
+    case 0: banded_lu_kernel<0><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
+    case 1: banded_lu_kernel<1><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
+    case 2: banded_lu_kernel<2><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
+    default: banded_lu_kernel<3><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
+  }
   return check_launch();
 }
 

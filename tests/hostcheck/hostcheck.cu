@@ -132,49 +132,46 @@ extern "C" int hostcheck_banded_lu(const double* wp, const double* t, int groups
         else b[4 + MST_NCOEF * (i - 1) + 6] = b[4 + MST_NCOEF * (i - 1) + 7] = v;
       }
     }
-    int singular_at = 0, jm = 0, sprev = WCOLS - 1;
+    int singular_at = 0;
     double rinv_prev = 0.0;
+    auto slot_of = [&](int col) { return W.data() + ((col + WCOLS) % WCOLS) * LD; };   // column -> its ring slot
     for (int j = 0; j < N; ++j) {
       double l[KL + 1];
       int jp;
       double rinv;
-      const bool ok = band_pivot(W.data() + jm * LD + KV, l, jp, rinv);
+      const bool ok = band_pivot<false>(slot_of(j) + KV, 0, l, jp, rinv);
       if (!ok && singular_at == 0) singular_at = j + 1;
       for (int lane = 0; lane < 32; ++lane) {
+        double leaves, enters;
+        band_retire_fetch(sys, slot_of(j - 1) + (lane < LD ? lane : LD - 1), j + KV + 1, lane, &leaves, &enters);
         if (ok) {
-          double* ptr = nullptr;
-          if (lane >= 1 && lane <= KV && j + lane < N) {
-            int sl = jm + lane;
-            if (sl >= WCOLS) sl -= WCOLS;
-            ptr = W.data() + sl * LD + KV - lane;
-          }
-          for (int q = lane - (KV + 1); q < R; q += 32 - (KV + 1)) {
-            if (q >= 0) ptr = Bs.data() + (size_t)q * NS + j;
-            if (ptr) band_update(ptr, jp, l);
-            if (q < 0) break;
+          if (lane < MAT_LANES) {
+            const int c = j + 1 + lane;
+            if (c < N) band_update(slot_of(c) + KV - (lane + 1), jp, l);
+          } else {
+            for (int q = lane - MAT_LANES; q < R; q += RHS_LANES) band_update(Bs.data() + (size_t)q * NS + j, jp, l);
           }
         }
         if (lane < LD && j + KV + 1 < N && band_entry_fast(sys, j + KV + 1, lane) != band_entry(sys, j + KV + 1, lane))
           return -2;   // the pattern tables must reproduce the rules they were derived from
-        band_retire(sys, W.data() + sprev * LD + (lane < LD ? lane : LD - 1),
-                    j > 0 ? Ug.data() + (size_t)(j - 1) * UROWS + (lane < KV ? lane : KV) : nullptr, j + KV + 1, lane,
-                    rinv_prev);
+        band_retire_store(sys, slot_of(j + KV + 1) + (lane < LD ? lane : LD - 1),
+                          Ug.data() + (size_t)(j > 0 ? j - 1 : 0) * UROWS + (lane < KV ? lane : KV), j == 0, j + KV + 1,
+                          lane, rinv_prev, leaves, enters);
       }
       rinv_prev = rinv;
-      sprev = jm;
-      jm = jm + 1 == WCOLS ? 0 : jm + 1;
     }
     for (int lane = 0; lane <= KV; ++lane)
-      Ug[(size_t)(N - 1) * UROWS + lane] = lane == KV ? rinv_prev : W[sprev * LD + lane];
+      Ug[(size_t)(N - 1) * UROWS + lane] = lane == KV ? rinv_prev : slot_of(N - 1)[lane];
     for (int j = N - 1; j >= 0; --j) {
       const double rinv = Ug[(size_t)j * UROWS + KV];
       for (int r = 0; r < R; ++r) {
-        const int d = r / K, k = r - d * K;
+        const int dd = r / K, k = r - dd * K;
         // lanes in DESCENDING order: a lane must not see what a lower lane wrote in this phase
         for (int lane = 31; lane >= 0; --lane) {
-          const double u = lane <= KV ? Ug[(size_t)j * UROWS + KV - lane] : 0.0;
-          band_backsub(Bs.data() + (size_t)r * NS + j, j < KV ? j : KV, lane, r % 32, u, rinv,
-                       coef + ((((size_t)g * G + d) * n + (j >> 3)) * K + k) * MST_NCOEF + (j & 7));
+          const int d = (lane < KV && lane < j) ? lane + 1 : 0;
+          const double u = d > 0 ? Ug[(size_t)j * UROWS + KV - d] : 0.0;
+          band_backsub(Bs.data() + (size_t)r * NS + j, d, lane, r % 32, u, rinv,
+                       coef + ((((size_t)g * G + dd) * n + (j >> 3)) * K + k) * MST_NCOEF + (j & 7));
         }
       }
     }

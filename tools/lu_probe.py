@@ -19,7 +19,10 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-for B, n, K, G in ((65536, 20, 3, 1), (262144, 10, 3, 1), (65536, 10, 4, 1), (65536 * 5, 10, 3, 5), (16384, 49, 3, 1)):
+CASES = ((65536, 20, 3, 1), (262144, 10, 3, 1), (65536, 10, 4, 1), (65536 * 5, 10, 3, 5), (16384, 49, 3, 1))
+if len(sys.argv) > 1:
+    CASES = CASES[:int(sys.argv[1])]
+for B, n, K, G in CASES:
     groups = B // G
     T = np.clip(rng.uniform(0.5, 2, (groups, n)) * np.exp(rng.normal(size=(groups, n))), 0.05, 5.0)
     t_np = np.concatenate([np.zeros((groups, 1)), np.cumsum(T, 1)], 1)
