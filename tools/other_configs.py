@@ -43,7 +43,9 @@ T=rng.uniform(0.6,1.6,(B,n)); t=torch.as_tensor(np.concatenate([np.zeros((B,1)),
 wp=torch.as_tensor(np.cumsum(rng.normal(0,1.0,(B,n+1,K)),1),device='cuda')
 iters=4
 mst.optimize_time_allocation(wp,t,iters=1); torch.cuda.synchronize()
-t0=time.perf_counter(); tn,cost=mst.optimize_time_allocation(wp,t,iters=iters); torch.cuda.synchronize(); dt=time.perf_counter()-t0
+dt=1e9
+for _ in range(3):   # wall clock (the search is host-driven): best of three
+    t0=time.perf_counter(); tn,cost=mst.optimize_time_allocation(wp,t,iters=iters); torch.cuda.synchronize(); dt=min(dt,time.perf_counter()-t0)
 print("config2 time-allocation search: %d problems x %d pieces, %d iterations: %.1f ms (%.1f ms / iteration, %.1f M re-solves/s); median cost ratio %.3f" % (
     B, n, iters, dt*1e3, dt*1e3/iters, B*6*iters/dt/1e6, float((cost[-1]/cost[0]).median())))
 # the benchmark's pipeline with the yaw axis as well (K = 4: rotated culls instead of the translation tables)
