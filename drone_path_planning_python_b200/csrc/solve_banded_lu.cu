@@ -79,13 +79,14 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
   double* pw = W + WCOLS * LD;                               // [n+1][8]
   double* Bs = pw + MST_NCOEF * (n + 1);                     // [R][NS]
   double* Ug = scratch + ((size_t)blockIdx.x * warps_per_block + warp) * UROWS * N;   // [N][UROWS]
+  const int todo = list ? *list_count : groups;
+  if (blockIdx.x * warps_per_block >= todo) return;   // nothing for this CTA (the usual case behind the condensed solver)
   for (int e = threadIdx.x; e < 64 + MST_NCOEF * LD; e += blockDim.x) band_table_entry(e, ff, cf, pi);
   __syncthreads();
   const BandSystem sys{n, N, pw, ff, cf, pi};
   const bool mat_lane = lane < MAT_LANES;           // owns column j + 1 + lane of the window
   const int rhs0 = lane - MAT_LANES;                // first right-hand side of the lane (if >= 0)
 
-  const int todo = list ? *list_count : groups;
   for (int item = blockIdx.x * warps_per_block + warp; item < todo;
        item += gridDim.x * warps_per_block) {
     const int g = list ? list[item] : item;
