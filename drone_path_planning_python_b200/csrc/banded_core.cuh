@@ -198,7 +198,7 @@ __host__ __device__ __forceinline__ void band_update(double* ptr, int jp, const 
 // newcol = j + kv + 1 takes the slot.  Lane l reads band position l and then writes band position l:
 // no other lane touches this slot during the step.
 // (slot and ucol already point at this lane's band position; first: j == 0, nothing leaves yet.)  In two
-// halves so that the kernel can issue the loads at the top of the step and the stores at its end.
+// halves, loads then stores (issuing the loads at the top of the step instead changed nothing).
 __host__ __device__ __forceinline__ void band_retire_fetch(const BandSystem& s, const double* slot, int newcol,
                                                            int lane, double* leaves, double* enters) {
   *leaves = 0.0;

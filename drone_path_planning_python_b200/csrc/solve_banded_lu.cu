@@ -57,7 +57,7 @@ __host__ size_t banded_lu_scratch_bytes(int groups, int n, int R) {
   return sizeof(double) * (size_t)banded_grid(p, groups) * p.warps * UROWS * MST_NCOEF * n;
 }
 
-// V: bit 0 = warp-wide pivot search, bit 1 = the refill's loads issued at the top of the step
+// V: 1 = warp-wide pivot search (default), 0 = every lane runs the comparison tree (banded_core.cuh)
 template <int V>
 __global__ void __launch_bounds__(BANDED_WARPS * 32, BANDED_MIN_CTAS)
 banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps,
@@ -173,15 +173,14 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
       double l[KL + 1];
       int jp;
       double rinv, leaves = 0.0, enters = 0.0;
-      if (V & 2) band_retire_fetch(sys, smem + leaving, j + KV + 1, lane, &leaves, &enters);   // loads off the critical path
-      if (band_pivot<(V & 1) != 0>(smem + colj, lane, l, jp, rinv)) {
+      if (band_pivot<V != 0>(smem + colj, lane, l, jp, rinv)) {
         if (live > 0) band_update(smem + mine, jp, l);
         if (rhs0 >= 0)   // more right-hand sides than lanes: the same row of every 15th one behind mine
           for (int m = RHS_LANES; rhs0 + m < R; m += RHS_LANES) band_update(smem + mine + (size_t)m * NS, jp, l);
       } else if (singular_at == 0) {
         singular_at = j + 1;
       }
-      if (!(V & 2)) band_retire_fetch(sys, smem + leaving, j + KV + 1, lane, &leaves, &enters);
+      band_retire_fetch(sys, smem + leaving, j + KV + 1, lane, &leaves, &enters);
       band_retire_store(sys, smem + entering, ucol, j == 0, j + KV + 1, lane, rinv_prev, leaves, enters);
       rinv_prev = rinv;
       --live;
@@ -272,9 +271,8 @@ int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K
   const BandedPlan p = banded_plan(n, G * K);
   if (p.warps == 0) return MST_ERR_TOO_LARGE;
   if (!scratch) return MST_ERR_INVALID;
-  static const int variant = getenv("MST_LU_VARIANT") ? atoi(getenv("MST_LU_VARIANT")) & 3 : BANDED_VARIANT;
-  const void* kernels[4] = {(const void*)banded_lu_kernel<0>, (const void*)banded_lu_kernel<1>,
-                            (const void*)banded_lu_kernel<2>, (const void*)banded_lu_kernel<3>};
+  static const int variant = getenv("MST_LU_VARIANT") ? atoi(getenv("MST_LU_VARIANT")) & 1 : BANDED_VARIANT;
+  const void* kernels[2] = {(const void*)banded_lu_kernel<0>, (const void*)banded_lu_kernel<1>};
   {
     const int rc = allow_dynamic_smem(kernels[variant], p.smem);
     if (rc != MST_OK) return rc;
@@ -282,9 +280,7 @@ int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K
   const unsigned grid = (unsigned)banded_grid(p, groups);
   switch (variant) {
     case 0: banded_lu_kernel<0><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
-    case 1: banded_lu_kernel<1><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
-    case 2: banded_lu_kernel<2><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
-    default: banded_lu_kernel<3><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
+    default: banded_lu_kernel<1><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
   }
   return check_launch();
 }

@@ -2,7 +2,7 @@
 TAG=${1:-lu}
 OUT=gpurun_out
 mkdir -p $OUT
-for v in 0 1 2 3; do
+for v in 0 1; do
   MST_LU_VARIANT=$v timeout 300 python tools/lu_probe.py 2 > $OUT/${TAG}_v$v.log 2>&1
   echo "variant $v rc=$?"; head -2 $OUT/${TAG}_v$v.log | cut -c1-120
 done
