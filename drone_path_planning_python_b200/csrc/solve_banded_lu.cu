@@ -212,6 +212,8 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
       // right-hand side r = d K + k is axis k of trajectory d of the group; lane r (mod 32) keeps where its
       // coefficients go and stores x_j itself
       double* const out0 = coef + (size_t)g * G * n * K * MST_NCOEF;
+      int bs_at = (int)(Bs - smem) + N - 1, ns = NS;   // row j of the first right-hand side; carried like the pointers above
+      asm volatile("" : "+r"(bs_at), "+r"(ns));
       const int next_traj = (n - 1) * K * MST_NCOEF + MST_NCOEF;   // from the last axis of one trajectory to the first of the next
       double* myout = out0 + ((size_t)(lane / K) * n * K + lane % K) * MST_NCOEF;
       for (int jc = N - 1; jc >= 0; jc -= 4) {
@@ -223,32 +225,33 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
           const int j = jc - i;   // N is a multiple of 8: never negative
           const double rinv = __shfl_sync(FULL, cu[i], KV);
           const int d = (lane < KV && lane < j) ? lane + 1 : 0;   // my row of U exists
-          double* bj = Bs + j;
+          double* bj = smem + bs_at;
+          --bs_at;
           const int colofs = (j >> 3) * K * MST_NCOEF + (j & 7);
           if (R <= 32) {
             int r = 0;
             for (; r + 3 <= R; r += 3) {   // three independent right-hand sides in flight (the axes of one drone)
-              const double x0 = bj[0] * rinv, x1 = bj[NS] * rinv, x2 = bj[2 * NS] * rinv;
+              const double x0 = bj[0] * rinv, x1 = bj[ns] * rinv, x2 = bj[2 * ns] * rinv;
               if (lane == r) myout[colofs] = x0;
               if (lane == r + 1) myout[colofs] = x1;
               if (lane == r + 2) myout[colofs] = x2;
               if (d > 0 && cu[i] != 0.0) {
-                const double b0 = bj[-d], b1 = bj[NS - d], b2 = bj[2 * NS - d];
+                const double b0 = bj[-d], b1 = bj[ns - d], b2 = bj[2 * ns - d];
                 bj[-d] = b0 - cu[i] * x0;
-                bj[NS - d] = b1 - cu[i] * x1;
-                bj[2 * NS - d] = b2 - cu[i] * x2;
+                bj[ns - d] = b1 - cu[i] * x1;
+                bj[2 * ns - d] = b2 - cu[i] * x2;
               }
-              bj += 3 * NS;
+              bj += 3 * ns;
             }
             for (; r < R; ++r) {
               band_backsub(bj, d, lane, r, cu[i], rinv, myout + colofs);
-              bj += NS;
+              bj += ns;
             }
           } else {
             double* out = out0 + colofs;
             for (int r = 0, k = 0; r < R; ++r) {
               band_backsub(bj, d, lane, 0, cu[i], rinv, out);
-              bj += NS;
+              bj += ns;
               out += MST_NCOEF;
               if (++k == K) { k = 0; out += next_traj - MST_NCOEF; }
             }
