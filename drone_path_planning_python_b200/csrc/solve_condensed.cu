@@ -152,8 +152,15 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
   const int col = lane - gl * R;
   const int d = col / K, k = col - d * K;
   const bool lane_used = gl < GPW;
-  // per-warp shared memory: rho[n][GPW] | fac[6(n-1)][GPW] | y[3(n-1)][32] | t[GPW][n+1] | wp[GPW*G][n+1][K]
-  const size_t per_warp = (size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) * (1 + R);
+  // per-warp shared memory: rho[n][GPW] | fac[6(n-1)][GPW] | y[3(n-1)][32] | t[GPW][n+1] | wp[n+1][WS]
+  // The waypoint tile is kept waypoint-major, one column of the warp per lane: lane c reads ww[i * WS + c], 32
+  // consecutive doubles per access (the trajectory-major order of the input put three lanes on every bank pair:
+  // half as many wavefronts again on the solver's most frequent shared-memory loads).  WS = 32 + K: consecutive
+  // elements of the input (axis fastest, then waypoint) land K apart per waypoint — the transposing stores are
+  // conflict free as well.
+  const int WS = 32 + K;
+  const size_t per_warp = (size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) +
+                          (size_t)(n + 1) * WS;
   double* wrho = sm + warp * per_warp;
   double* wfac = wrho + (size_t)GPW * n;
   double* wy = wfac + (size_t)GPW * 6 * (n - 1);
@@ -168,6 +175,15 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
   // the solve.  Used when a set's inputs fit the register tile.
   const bool piped = GPW * (n + 1) <= 32 * COLS_TREGS && GPW * (n + 1) * R <= 32 * COLS_WREGS;
   double tr[COLS_TREGS], wr[COLS_WREGS];
+  // where element e = [trajectory][waypoint][axis] of a set's waypoint slice goes in the tile
+  auto tile_slot = [&](int e) {
+    const int tt = e / ((n + 1) * K), rem = e - tt * (n + 1) * K;
+    const int i = rem / K;
+    return i * WS + tt * K + (rem - i * K);
+  };
+  int wdst[COLS_WREGS];
+#pragma unroll
+  for (int j = 0; j < COLS_WREGS; ++j) wdst[j] = tile_slot(lane + 32 * j);
   auto load_set = [&](long long set2) {
     if (set2 >= sets) return;
     const long long h0 = set2 * GPW;
@@ -189,10 +205,10 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
 #pragma unroll
       for (int j = 0; j < COLS_TREGS; ++j) if (lane + 32 * j < cnt * (n + 1)) wt[lane + 32 * j] = tr[j];
 #pragma unroll
-      for (int j = 0; j < COLS_WREGS; ++j) if (lane + 32 * j < cnt * (n + 1) * R) ww[lane + 32 * j] = wr[j];
+      for (int j = 0; j < COLS_WREGS; ++j) if (lane + 32 * j < cnt * (n + 1) * R) ww[wdst[j]] = wr[j];
     } else {
       for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = tstamps[(size_t)g0 * (n + 1) + i];
-      for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[i] = wp[(size_t)g0 * (n + 1) * R + i];
+      for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[tile_slot(i)] = wp[(size_t)g0 * (n + 1) * R + i];
     }
     __syncwarp();
     if (piped) load_set(set + (long long)gridDim.x * warps);
@@ -237,10 +253,10 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
       if (k == 0) info[traj] = cls == 2 ? MST_INFO_DECREASING : (cls == 3 ? MST_INFO_NONFINITE : (cls == 4 ? 1 : MST_INFO_DECLINED));
       continue;
     }
-    const double* wcol = ww + ((size_t)gl * G + d) * (n + 1) * K + k;
-    condensed_forward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
+    const double* wcol = ww + lane;   // lane = (gl G + d) K + k: its column of the tile
+    condensed_forward<1>(wcol, WS, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32);
     unsigned farbits = 0u;
-    condensed_backward<1>(wcol, K, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32,
+    condensed_backward<1>(wcol, WS, n, 1, wrho + gl, wfac + gl, GPW, wy + lane, 32,
                           [&](int piece, int, const double* c, double) {
                             double2* dst = reinterpret_cast<double2*>(cd + (size_t)piece * K * MST_NCOEF);
                             dst[0] = make_double2(c[0], c[1]);
@@ -276,7 +292,8 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
 
 static size_t cols_smem_per_warp(int n, int K, int G) {
   const int R = G * K, GPW = 32 / R;
-  return sizeof(double) * ((size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) * (1 + R));
+  return sizeof(double) * ((size_t)GPW * (n + 6 * (n - 1)) + 32 * (size_t)(3 * (n - 1)) + (size_t)GPW * (n + 1) +
+                           (size_t)(n + 1) * (32 + K));
 }
 
 // cull (may be null): far-piece bits for the pipeline's sampling kernel (cull->mask, honoured with n <= 32;
