@@ -351,20 +351,24 @@ __host__ __device__ __forceinline__ bool collide_engine_supports(const MeshView&
 
 // Translation-only poses: tables of the env planes against the robot's unique vertices, which a
 // translation leaves constant (the signed distance of a moved vertex is then one add).  Four
-// rows of V per env triangle: nv[(4 e + 0) V + v] = n_e . vertex_v (the triangle's plane),
-// nv[(4 e + 1 + k) V + v] = m_ek . vertex_v (edge plane k).  Every thread of the CTA calls it,
-// followed by a CTA barrier.
+// rows of V per env triangle: nv[e TS + 0 V + v] = n_e . vertex_v (the triangle's plane),
+// nv[e TS + (1 + k) V + v] = m_ek . vertex_v (edge plane k).  TS = 4 V made odd: the lanes of a warp walk
+// DIFFERENT triangles e at the same v, and with TS a multiple of 16 doubles (V = 8: the benchmark's robot) they
+// all met on one bank pair — 1.8 wavefronts per load on the engine's most frequent shared-memory access.  Every
+// thread of the CTA calls the builder, followed by a CTA barrier.
 constexpr int COLLIDE_TABLE_ROWS = 4;
+__host__ __device__ __forceinline__ int collide_table_stride(int robotV) { return (COLLIDE_TABLE_ROWS * robotV) | 1; }
 __host__ __device__ __forceinline__ size_t collide_table_doubles(int envT, int robotV) {
-  return (size_t)COLLIDE_TABLE_ROWS * envT * robotV;
+  return ((size_t)envT * collide_table_stride(robotV) + 1) & ~(size_t)1;   // what follows stays 16-byte aligned
 }
 __device__ __forceinline__ void build_plane_vertex_table(const MeshView& rb, const MeshView& ev, double* nv) {
+  const int TS = collide_table_stride(rb.V);
   for (int i = threadIdx.x; i < COLLIDE_TABLE_ROWS * ev.T * rb.V; i += blockDim.x) {
     const int row = i / rb.V, v = i - row * rb.V;
     const int e = row >> 2, j = row & 3;
     const double* pl = j == 0 ? ev.plane + 4 * e : ev.edge + 12 * e + 4 * (j - 1);
     const double* p = rb.vert + 3 * v;
-    nv[i] = pl[0] * p[0] + pl[1] * p[1] + pl[2] * p[2];
+    nv[e * TS + j * rb.V + v] = pl[0] * p[0] + pl[1] * p[1] + pl[2] * p[2];
   }
 }
 
@@ -549,7 +553,7 @@ __device__ __forceinline__ void ring_drain(PoseRing<PoseDim<POSE>::N>& ring, uns
           const double o1 = ed[4] * pp[0] + ed[5] * pp[1] + ed[6] * pp[2] - ed[7];
           const double o2 = ed[8] * pp[0] + ed[9] * pp[1] + ed[10] * pp[2] - ed[11];
           if (POSE == 0 && TABLE) {
-            const double* row = nv + (size_t)e * COLLIDE_TABLE_ROWS * rb.V;
+            const double* row = nv + (size_t)e * collide_table_stride(rb.V);
             for (int v = 0; v < rb.V; ++v) {
               const double dist = row[v] + off;
               const unsigned tv = rb.vtri[v];
