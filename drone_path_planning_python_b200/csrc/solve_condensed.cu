@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "farcull.cuh"
 #include "stage.cuh"
 
@@ -133,13 +135,14 @@ condensed_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
 // trajectory write adjacent 64-byte coefficient rows and read adjacent waypoint values.
 // Inputs of the warp's groups are one contiguous range each: copied into shared memory with
 // coalesced loads before use.
+constexpr int COLS_MAX_WARPS = 7;
 constexpr int COLS_TREGS = 4, COLS_WREGS = 12;  // register tile of the input pipeline, doubles per lane
 
 // CULL = true (pipeline, n <= 32): every lane also bounds its pieces' positions while their coefficients are
 // in registers and writes the far-piece bits of its axis (farcull.cuh) for the sampling kernel.
 // MAT = true: the float32 polynomial matrix rows as a second output (FarCull::mat).
 template <bool CULL, bool MAT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(COLS_MAX_WARPS * 32, 2)   // two CTAs of seven warps: 14 warps per SM need <= 146 registers
 condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps, int groups, int n,
                       int K, int G, int force, double* __restrict__ coef, double* __restrict__ dur,
                       int* __restrict__ info, int* __restrict__ list, int* __restrict__ list_count, FarCull cull) {
@@ -175,15 +178,31 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
   // the solve.  Used when a set's inputs fit the register tile.
   const bool piped = GPW * (n + 1) <= 32 * COLS_TREGS && GPW * (n + 1) * R <= 32 * COLS_WREGS;
   double tr[COLS_TREGS], wr[COLS_WREGS];
-  // where element e = [trajectory][waypoint][axis] of a set's waypoint slice goes in the tile
-  auto tile_slot = [&](int e) {
-    const int tt = e / ((n + 1) * K), rem = e - tt * (n + 1) * K;
-    const int i = rem / K;
-    return i * WS + tt * K + (rem - i * K);
+  // where element e = [trajectory][waypoint][axis] of a set's waypoint slice goes in the tile: a lane's
+  // elements are 32 apart, (trajectory, waypoint, axis) advance by carries instead of divisions
+  const int step_k = 32 % K, step_i = 32 / K;
+  struct TileWalk { int tt, i, k; };
+  auto walk_start = [&]() {
+    TileWalk w;
+    w.tt = lane / ((n + 1) * K);
+    const int rem = lane - w.tt * (n + 1) * K;
+    w.i = rem / K;
+    w.k = rem - w.i * K;
+    return w;
+  };
+  auto walk_slot = [&](const TileWalk& w) { return w.i * WS + w.tt * K + w.k; };
+  auto walk_next = [&](TileWalk& w) {
+    w.k += step_k;
+    w.i += step_i;
+    if (w.k >= K) { w.k -= K; ++w.i; }
+    while (w.i > n) { w.i -= n + 1; ++w.tt; }
   };
   int wdst[COLS_WREGS];
+  {
+    TileWalk w = walk_start();
 #pragma unroll
-  for (int j = 0; j < COLS_WREGS; ++j) wdst[j] = tile_slot(lane + 32 * j);
+    for (int j = 0; j < COLS_WREGS; ++j) { wdst[j] = walk_slot(w); walk_next(w); }
+  }
   auto load_set = [&](long long set2) {
     if (set2 >= sets) return;
     const long long h0 = set2 * GPW;
@@ -208,7 +227,11 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
       for (int j = 0; j < COLS_WREGS; ++j) if (lane + 32 * j < cnt * (n + 1) * R) ww[wdst[j]] = wr[j];
     } else {
       for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = tstamps[(size_t)g0 * (n + 1) + i];
-      for (int i = lane; i < cnt * (n + 1) * R; i += 32) ww[tile_slot(i)] = wp[(size_t)g0 * (n + 1) * R + i];
+      TileWalk w = walk_start();
+      for (int i = lane; i < cnt * (n + 1) * R; i += 32) {
+        ww[walk_slot(w)] = wp[(size_t)g0 * (n + 1) * R + i];
+        walk_next(w);
+      }
     }
     __syncwarp();
     if (piped) load_set(set + (long long)gridDim.x * warps);
@@ -296,6 +319,28 @@ static size_t cols_smem_per_warp(int n, int K, int G) {
                            (size_t)(n + 1) * (32 + K));
 }
 
+// The occupancy search behind the launcher's choice of warps per CTA, remembered per (kernel, shared memory per
+// warp): a dozen driver calls, too many for every launch of a single-trajectory solve.
+static int cols_warps_per_cta(const void* kern, size_t per_warp, int* resident_ctas) {
+  struct Entry { const void* kern; size_t per_warp; int wpb, ctas; };
+  static Entry cache[32];
+  static int used = 0;
+  static std::mutex lock;
+  std::lock_guard<std::mutex> guard(lock);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].kern == kern && cache[i].per_warp == per_warp) { *resident_ctas = cache[i].ctas; return cache[i].wpb; }
+  int wpb = 1, best = 0, best_ctas = 1;
+  for (int w = 1; w <= COLS_MAX_WARPS && w * per_warp + 64 <= MST_MAX_SMEM; ++w) {
+    if (allow_dynamic_smem(kern, w * per_warp) != MST_OK) break;
+    int ctas = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 32 * w, w * per_warp) != cudaSuccess) break;
+    if (ctas * w > best) { best = ctas * w; wpb = w; best_ctas = ctas; }
+  }
+  if (used < 32) cache[used++] = Entry{kern, per_warp, wpb, best_ctas};
+  *resident_ctas = best_ctas;
+  return wpb;
+}
+
 // cull (may be null): far-piece bits for the pipeline's sampling kernel (cull->mask, honoured with n <= 32;
 // the caller zeroes the mask beforehand, so groups solved any other way simply have no far pieces) and / or
 // the float32 polynomial matrix (cull->mat).  Returns MST_ERR_TOO_LARGE when a matrix is asked for and the
@@ -312,9 +357,7 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
   static const bool use_cols = getenv("MST_CONDENSED_THREAD_PER_GROUP") == nullptr;
   if (use_cols && G * K <= 32 && n >= 1) {
     const size_t per_warp = cols_smem_per_warp(n, K, G);
-    // warps per CTA: small CTAs pack the SM's shared memory best (warps are independent)
-    const int wpb = 2 * per_warp + 64 <= MST_MAX_SMEM ? 2 : 1;
-    if (wpb * per_warp + 64 <= MST_MAX_SMEM) {
+    if (per_warp + 64 <= MST_MAX_SMEM) {
       const int GPW = 32 / (G * K);
       const long long sets = ((long long)groups + GPW - 1) / GPW;
       const bool culling = cull != nullptr && cull->mask != nullptr && n <= 32;
@@ -323,10 +366,20 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
                           : (packing ? condensed_cols_kernel<false, true> : condensed_cols_kernel<false, false>);
       FarCull fc;
       if (cull) fc = *cull; else memset(&fc, 0, sizeof(fc));
+      // warps per CTA (the warps are independent): whatever keeps most warps resident — every CTA pays 1 kB of
+      // reserved shared memory, so few large CTAs pack an SM better than many small ones (n = 10, K = 3: two CTAs
+      // of 7 warps = 14 warps, against 12 with CTAs of 2)
+      int resident = 1;
+      const int wpb = cols_warps_per_cta((const void*)kern, per_warp, &resident);
       const int rc = allow_dynamic_smem((const void*)kern, wpb * per_warp);
       if (rc != MST_OK) return rc;
       long long blocks = (sets + wpb - 1) / wpb;
-      const long long cap = (long long)MST_SM_COUNT * 16;
+      // many more CTAs than fit at once: the hardware scheduler then evens out the SMs (measured per 1 M
+      // trajectories: 7 CTAs per SM = one wave 1.00 ms, 16: 1.00, 32: 0.92, 64: 0.90, 128: 0.885, one CTA per
+      // 2 sets: 0.90; tools/gpu_cols_ab.sh)
+      static const int per_sm_env = getenv("MST_COLS_CTAS_PER_SM") ? atoi(getenv("MST_COLS_CTAS_PER_SM")) : 0;   // A/B
+      (void)resident;
+      const long long cap = (long long)MST_SM_COUNT * (per_sm_env > 0 ? per_sm_env : 128);
       if (blocks > cap) blocks = cap;
       if (blocks < 1) blocks = 1;
       kern<<<(unsigned)blocks, 32 * wpb, wpb * per_warp, stream>>>(wp, t, groups, n, K, G, force, coef, dur, info, list,
