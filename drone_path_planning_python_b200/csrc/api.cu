@@ -56,7 +56,7 @@ int launch_condensed(const double* wp, const double* t, int groups, int n, int K
                      cudaStream_t stream, const FarCull* cull = nullptr);
 int launch_sample_collide_cull(const double* coef, const double* dur, const unsigned* far_mask, int B, int n, int K,
                                int S, const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
-                               cudaStream_t stream);
+                               int* tile_counter, cudaStream_t stream);
 bool sample_collide_cull_suits(int n, int K, int S, const mst_mesh* robot, const mst_mesh* env);
 int launch_sample(const double* coef, const double* dur, int B, int n, int K, const double* ts,
                   int ts_per_traj, int S, int mode, int deriv, double* out, uint8_t* status,
@@ -391,7 +391,7 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
         }
       }
       if (stage == 1) continue;
-      rc = launch_sample_collide_cull(cc, dd, fc.mask, nb, n, K, S, robot, env, hh, aa, st);
+      rc = launch_sample_collide_cull(cc, dd, fc.mask, nb, n, K, S, robot, env, hh, aa, (int*)workspace + 32, st);   // counters[32]: tile tickets
       if (rc == MST_OK) continue;
       if (rc != MST_ERR_TOO_LARGE) return rc;
       rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st);

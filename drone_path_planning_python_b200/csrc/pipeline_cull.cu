@@ -30,7 +30,7 @@ sample_collide_cull_kernel(const double* __restrict__ coef, const double* __rest
                            const unsigned* __restrict__ far_mask, int B, int n, int S, int WT,
                            const void* __restrict__ robot_img, MeshLayout rl, MeshBounds rbb,
                            const void* __restrict__ env_img, MeshLayout el, MeshBounds evb,
-                           uint8_t* __restrict__ hit, uint8_t* __restrict__ any_hit) {
+                           uint8_t* __restrict__ hit, uint8_t* __restrict__ any_hit, int* __restrict__ next_tile) {
   constexpr int POSE = K == 3 ? 0 : 1;
   constexpr int NP = PoseDim<POSE>::N;
   const unsigned FULL = 0xffffffffu;
@@ -61,8 +61,16 @@ sample_collide_cull_kernel(const double* __restrict__ coef, const double* __rest
     if (h) { hit[(size_t)b * S + s] = 1; any_hit[b] = 1; }   // rows were zero-filled
   };
 
+  // Tiles are handed out by a device counter (zeroed by the launcher): the work of a tile depends on how many of
+  // its samples are near the obstacles, and with a fixed stride over the tiles the kernel waited for its unluckiest
+  // warp.  The next ticket is drawn while the current tile is processed.
   const int tiles = (B + WT - 1) / WT;
-  for (int tile = blockIdx.x * CULL_WARPS + warp; tile < tiles; tile += gridDim.x * CULL_WARPS) {
+  const int first = blockIdx.x * CULL_WARPS + warp, all_warps = gridDim.x * CULL_WARPS;
+  int ticket = 0;
+  if (next_tile != nullptr && lane == 0) ticket = atomicAdd(next_tile, 1);
+  for (int tile = next_tile != nullptr ? __shfl_sync(FULL, ticket, 0) : first; tile < tiles;
+       tile = next_tile != nullptr ? __shfl_sync(FULL, ticket, 0) : tile + all_warps) {
+    if (next_tile != nullptr && lane == 0) ticket = atomicAdd(next_tile, 1);
     const int b0 = tile * WT;
     const int nb = min(WT, B - b0);
     __syncwarp();  // previous tile's tables are no longer read
@@ -201,10 +209,11 @@ bool sample_collide_cull_suits(int n, int K, int S, const mst_mesh* robot, const
   return cull_mesh_bytes(K, robot, env) + CULL_WARPS * WT * per_traj <= 56 * 1024;
 }
 
-// MST_ERR_TOO_LARGE when the sizes do not suit this kernel (the caller runs sample_collide_kernel)
+// MST_ERR_TOO_LARGE when the sizes do not suit this kernel (the caller runs sample_collide_kernel).
+// tile_counter (device int, may be null: fixed stride over the tiles): scratch for the tile tickets.
 int launch_sample_collide_cull(const double* coef, const double* dur, const unsigned* far_mask, int B, int n, int K,
                                int S, const mst_mesh* robot, const mst_mesh* env, uint8_t* hit, uint8_t* any_hit,
-                               cudaStream_t stream) {
+                               int* tile_counter, cudaStream_t stream) {
   if (B == 0) return MST_OK;
   if (!sample_collide_cull_suits(n, K, S, robot, env)) return MST_ERR_TOO_LARGE;
   const size_t mesh_bytes = cull_mesh_bytes(K, robot, env);
@@ -218,10 +227,18 @@ int launch_sample_collide_cull(const double* coef, const double* dur, const unsi
   }
   const int tiles = (B + WT - 1) / WT;
   int blocks = (tiles + CULL_WARPS - 1) / CULL_WARPS;
-  const int cap = MST_SM_COUNT * 4;  // persistent CTAs (4 resident per SM); warps stride over the tiles
+  static const int per_sm_env = getenv("MST_CULL_CTAS_PER_SM") ? atoi(getenv("MST_CULL_CTAS_PER_SM")) : 0;   // A/B
+  const int cap = MST_SM_COUNT * (per_sm_env > 0 ? per_sm_env : 4);  // 4 resident per SM; warps stride over the tiles
   if (blocks > cap) blocks = cap;
+  static const bool fixed_stride = getenv("MST_CULL_FIXED_STRIDE") != nullptr;   // A/B
+  if (fixed_stride) tile_counter = nullptr;
+  if (tile_counter != nullptr) {
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  }
   kern<<<blocks, CULL_THREADS, smem, stream>>>(coef, dur, far_mask, B, n, S, WT, robot->d_image, robot->layout,
-                                               robot->bounds, env->d_image, env->layout, env->bounds, hit, any_hit);
+                                               robot->bounds, env->d_image, env->layout, env->bounds, hit, any_hit,
+                                               tile_counter);
   return check_launch();
 }
 
