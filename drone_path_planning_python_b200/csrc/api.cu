@@ -47,7 +47,7 @@ int allow_dynamic_smem(const void* kernel, size_t dynamic_bytes) {
 // kernels' host launchers (one per .cu file)
 size_t banded_lu_smem_per_warp(int n, int R);
 int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K, int G, const int* list,
-                     const int* list_count, double* coef, double* dur, int* info, double* scratch,
+                     const int* list_count, double* coef, double* dur, int* info, double* scratch, int* ticket,
                      cudaStream_t stream);
 size_t banded_lu_scratch_bytes(int groups, int n, int R);
 size_t condensed_workspace_bytes(int groups);
@@ -215,14 +215,14 @@ static int solve_impl(const double* wp, const double* t, int B, int n, int K, in
   if (!banded_fits && solver == MST_SOLVER_AUTO) solver = MST_SOLVER_CONDENSED;
   if (!workspace) return MST_ERR_INVALID;
   if (solver == MST_SOLVER_BANDED_LU)
-    return launch_banded_lu(wp, t, groups, n, K, G, nullptr, nullptr, coef, dur, info, lu_scratch(workspace, groups), st);
+    return launch_banded_lu(wp, t, groups, n, K, G, nullptr, nullptr, coef, dur, info, lu_scratch(workspace, groups), (int*)workspace + 33, st);
   int* list_count = (int*)workspace;
   int* list = list_count + 64;
   int rc = launch_condensed(wp, t, groups, n, K, G, solver == MST_SOLVER_CONDENSED, coef, dur, info,
                             list, list_count, st, cull);
   if (rc != MST_OK || solver == MST_SOLVER_CONDENSED) return rc;
   // groups the condensed path declined (duration spread too wide, t[0] != 0, bad input)
-  return launch_banded_lu(wp, t, groups, n, K, G, list, list_count, coef, dur, info, lu_scratch(workspace, groups), st);
+  return launch_banded_lu(wp, t, groups, n, K, G, list, list_count, coef, dur, info, lu_scratch(workspace, groups), (int*)workspace + 33, st);
 }
 
 extern "C" int mst_sample_batch(const double* coef, const double* dur, int B, int n, int K,
@@ -339,7 +339,7 @@ static int pipeline_impl(const double* wp, const double* t, int B, int n, int K,
                           wire ? &wchunk : nullptr, st);
       if (rc == MST_OK) {
         // groups the condensed path must not take: pivoted solve, then their samples (list mode)
-        rc = launch_banded_lu(wc, tc, nb / G, n, K, G, list, counters, cc, dd, info + b0, lu_scratch(workspace, nb / G), st);
+        rc = launch_banded_lu(wc, tc, nb / G, n, K, G, list, counters, cc, dd, info + b0, lu_scratch(workspace, nb / G), (int*)workspace + 33, st);
         if (rc != MST_OK) return rc;
         rc = launch_sample_collide(cc, dd, nb, n, K, S, robot, env, hh, aa, st, list, counters, G);
         if (rc != MST_OK) return rc;

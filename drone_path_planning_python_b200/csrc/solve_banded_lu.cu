@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(BANDED_WARPS * 32, BANDED_MIN_CTAS)
 banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstamps,
                  int groups, int n, int K, int G, const int* __restrict__ list,
                  const int* __restrict__ list_count, double* __restrict__ coef,
-                 double* __restrict__ dur, int* __restrict__ info, double* __restrict__ scratch) {
+                 double* __restrict__ dur, int* __restrict__ info, double* __restrict__ scratch,
+                 int* __restrict__ ticket) {
   extern __shared__ double smem[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -87,8 +88,13 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
   const bool mat_lane = lane < MAT_LANES;           // owns column j + 1 + lane of the window
   const int rhs0 = lane - MAT_LANES;                // first right-hand side of the lane (if >= 0)
 
-  for (int item = blockIdx.x * warps_per_block + warp; item < todo;
-       item += gridDim.x * warps_per_block) {
+  // groups are handed out by a device counter (null: fixed stride): equal work per group, but the SMs do not
+  // run equally fast, and a fixed share per warp waits for the slowest
+  int drawn = 0;
+  if (ticket != nullptr && lane == 0) drawn = atomicAdd(ticket, 1);
+  for (int item = ticket != nullptr ? __shfl_sync(FULL, drawn, 0) : blockIdx.x * warps_per_block + warp; item < todo;
+       item = ticket != nullptr ? __shfl_sync(FULL, drawn, 0) : item + gridDim.x * warps_per_block) {
+    if (ticket != nullptr && lane == 0) drawn = atomicAdd(ticket, 1);
     const int g = list ? list[item] : item;
     const double* tg = tstamps + (size_t)g * (n + 1);
 
@@ -267,10 +273,10 @@ banded_lu_kernel(const double* __restrict__ wp, const double* __restrict__ tstam
 }
 
 // host launcher; list/list_count (device) restrict the work to listed groups when non-null;
-// scratch: banded_lu_scratch_bytes(groups, n, G*K) bytes of device memory
+// scratch: banded_lu_scratch_bytes(groups, n, G*K) bytes of device memory; ticket: one device int (may be null)
 int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K, int G,
                      const int* list, const int* list_count, double* coef, double* dur,
-                     int* info, double* scratch, cudaStream_t stream) {
+                     int* info, double* scratch, int* ticket, cudaStream_t stream) {
   const BandedPlan p = banded_plan(n, G * K);
   if (p.warps == 0) return MST_ERR_TOO_LARGE;
   if (!scratch) return MST_ERR_INVALID;
@@ -281,9 +287,15 @@ int launch_banded_lu(const double* wp, const double* t, int groups, int n, int K
     if (rc != MST_OK) return rc;
   }
   const unsigned grid = (unsigned)banded_grid(p, groups);
+  static const bool fixed_stride = getenv("MST_LU_FIXED_STRIDE") != nullptr;   // A/B
+  if (fixed_stride) ticket = nullptr;
+  if (ticket != nullptr) {
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(int), stream);
+    if (e != cudaSuccess) { note_cuda_error(e); return MST_ERR_CUDA; }
+  }
   switch (variant) {
-    case 0: banded_lu_kernel<0><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
-    default: banded_lu_kernel<1><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch); break;
+    case 0: banded_lu_kernel<0><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch, ticket); break;
+    default: banded_lu_kernel<1><<<grid, p.warps * 32, p.smem, stream>>>(wp, t, groups, n, K, G, list, list_count, coef, dur, info, scratch, ticket); break;
   }
   return check_launch();
 }
