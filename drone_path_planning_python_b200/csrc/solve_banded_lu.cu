@@ -25,7 +25,7 @@ __host__ size_t banded_lu_smem_per_warp(int n, int R) { return sizeof(double) * 
 struct BandedPlan {
   int warps;        // per CTA
   size_t smem;      // dynamic shared memory per CTA
-  int ctas_per_sm;  // resident CTAs the shared memory and the 64-register bound allow
+  int ctas_per_sm;  // resident CTAs the shared memory and the 80-register bound allow
 };
 
 // 0 warps: one group does not fit an SM's shared memory
