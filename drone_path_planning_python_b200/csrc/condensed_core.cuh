@@ -311,4 +311,27 @@ __host__ __device__ inline int classify_times(const double* tg, int n, double* T
   return 0;
 }
 
+// Walk over the elements e, e + 32, e + 64, ... of a contiguous waypoint slice [trajectory][waypoint 0..n][axis
+// 0..K-1] (what one lane of a warp copies): (trajectory, waypoint, axis) advance by carries instead of two
+// divisions per element.  slot(): where the element goes in a waypoint-major tile of row stride WS whose columns
+// are (trajectory, axis) pairs — the layout the lane-per-column solver reads without bank conflicts.
+struct TileWalk {
+  int tt, i, k;
+  __host__ __device__ static TileWalk start(int e, int n, int K) {
+    TileWalk w;
+    w.tt = e / ((n + 1) * K);
+    const int rem = e - w.tt * (n + 1) * K;
+    w.i = rem / K;
+    w.k = rem - w.i * K;
+    return w;
+  }
+  __host__ __device__ int slot(int WS, int K) const { return i * WS + tt * K + k; }
+  __host__ __device__ void advance32(int n, int K) {
+    k += 32 % K;
+    i += 32 / K;
+    if (k >= K) { k -= K; ++i; }
+    while (i > n) { i -= n + 1; ++tt; }
+  }
+};
+
 }  // namespace mst

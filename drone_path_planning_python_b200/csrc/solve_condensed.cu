@@ -178,30 +178,14 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
   // the solve.  Used when a set's inputs fit the register tile.
   const bool piped = GPW * (n + 1) <= 32 * COLS_TREGS && GPW * (n + 1) * R <= 32 * COLS_WREGS;
   double tr[COLS_TREGS], wr[COLS_WREGS];
-  // where element e = [trajectory][waypoint][axis] of a set's waypoint slice goes in the tile: a lane's
-  // elements are 32 apart, (trajectory, waypoint, axis) advance by carries instead of divisions
-  const int step_k = 32 % K, step_i = 32 / K;
-  struct TileWalk { int tt, i, k; };
-  auto walk_start = [&]() {
-    TileWalk w;
-    w.tt = lane / ((n + 1) * K);
-    const int rem = lane - w.tt * (n + 1) * K;
-    w.i = rem / K;
-    w.k = rem - w.i * K;
-    return w;
-  };
-  auto walk_slot = [&](const TileWalk& w) { return w.i * WS + w.tt * K + w.k; };
-  auto walk_next = [&](TileWalk& w) {
-    w.k += step_k;
-    w.i += step_i;
-    if (w.k >= K) { w.k -= K; ++w.i; }
-    while (w.i > n) { w.i -= n + 1; ++w.tt; }
-  };
+  // where element e = [trajectory][waypoint][axis] of a set's waypoint slice goes in the tile (TileWalk,
+  // condensed_core.cuh): a lane's elements are 32 apart
+  const TileWalk walk0 = TileWalk::start(lane, n, K);
   int wdst[COLS_WREGS];
   {
-    TileWalk w = walk_start();
+    TileWalk w = walk0;
 #pragma unroll
-    for (int j = 0; j < COLS_WREGS; ++j) { wdst[j] = walk_slot(w); walk_next(w); }
+    for (int j = 0; j < COLS_WREGS; ++j) { wdst[j] = w.slot(WS, K); w.advance32(n, K); }
   }
   auto load_set = [&](long long set2) {
     if (set2 >= sets) return;
@@ -227,10 +211,10 @@ condensed_cols_kernel(const double* __restrict__ wp, const double* __restrict__ 
       for (int j = 0; j < COLS_WREGS; ++j) if (lane + 32 * j < cnt * (n + 1) * R) ww[wdst[j]] = wr[j];
     } else {
       for (int i = lane; i < cnt * (n + 1); i += 32) wt[i] = tstamps[(size_t)g0 * (n + 1) + i];
-      TileWalk w = walk_start();
+      TileWalk w = walk0;
       for (int i = lane; i < cnt * (n + 1) * R; i += 32) {
-        ww[walk_slot(w)] = wp[(size_t)g0 * (n + 1) * R + i];
-        walk_next(w);
+        ww[w.slot(WS, K)] = wp[(size_t)g0 * (n + 1) * R + i];
+        w.advance32(n, K);
       }
     }
     __syncwarp();

@@ -179,3 +179,15 @@ extern "C" int hostcheck_banded_lu(const double* wp, const double* t, int groups
   }
   return 0;
 }
+
+// TileWalk (condensed_core.cuh) against the direct index arithmetic: slots[e] for e = lane, lane + 32, ...
+extern "C" int hostcheck_tile_walk(int n, int K, int WS, int total, int* slots) {
+  for (int lane = 0; lane < 32; ++lane) {
+    TileWalk w = TileWalk::start(lane, n, K);
+    for (int e = lane; e < total; e += 32) {
+      slots[e] = w.slot(WS, K);
+      w.advance32(n, K);
+    }
+  }
+  return 0;
+}

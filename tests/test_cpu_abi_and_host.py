@@ -422,3 +422,19 @@ def test_banded_window_lu_reports_the_zero_pivot():
     gbsv, = sl.get_lapack_funcs(("gbsv",), (ab,))
     _, _, _, lapack_info = gbsv(10, 7, ab, rhs.copy())
     assert lapack_info > 0 and int(info[0]) == lapack_info
+
+
+@pytest.mark.parametrize("n,K,traj", [(1, 1, 32), (1, 4, 8), (2, 2, 16), (10, 3, 10), (10, 4, 8), (20, 3, 10), (49, 3, 10), (300, 1, 32)])
+def test_tile_walk_matches_direct_indexing(n, K, traj):
+    """The condensed solver copies a set's waypoints [trajectory][waypoint][axis] into a waypoint-major tile
+    (column = trajectory x axis, row stride WS = 32 + K); its carry-based index walk must give i * WS + t * K + k
+    for every element, and the tile must be collision free."""
+    lib = _hostcheck()
+    WS = 32 + K
+    total = traj * (n + 1) * K
+    slots = np.full(total, -1, dtype=np.int32)
+    assert lib.hostcheck_tile_walk(n, K, WS, total, P(slots.ctypes.data)) == 0
+    e = np.arange(total)
+    t, rem = e // ((n + 1) * K), e % ((n + 1) * K)
+    assert np.array_equal(slots, (rem // K) * WS + t * K + rem % K)
+    assert len(np.unique(slots)) == total and slots.max() < (n + 1) * WS
